@@ -1,0 +1,112 @@
+"""Helpers shared by the parity tests: load a golden case, run the oracle on it, error norms."""
+import glob
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def case_names(prefix):
+    return sorted(
+        os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, prefix + "*.npz"))
+    )
+
+
+def load_case(name, device="cpu", dtype=torch.float32):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    out = {}
+    for k in z.files:
+        v = z[k]
+        if v.dtype.kind == "f" and v.ndim > 0 and not k.startswith("cfg"):
+            out[k] = torch.from_numpy(v.astype(np.float32)).to(device=device, dtype=dtype)
+        elif k in ("grid_idx",):
+            out[k] = torch.from_numpy(v.astype(np.int32)).to(device)
+        else:
+            out[k] = v
+    return out
+
+
+def rel_err(a, b):
+    """mean|a-b| / mean|b| -- the robust norm of SURVEY.md 8d."""
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    return float((a - b).abs().mean() / b.abs().mean().clamp_min(1e-30))
+
+
+def max_err(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def renderer_cfg(c):
+    num_samples, num_samples_inf, mask_oob, contract, noise_seed = (int(v) for v in c["cfg"])
+    gain, disp, sigma = (float(v) for v in c["cfg_f"])
+    return dict(num_samples=num_samples, num_samples_inf=num_samples_inf,
+                mask_out_of_bounds_samples=bool(mask_oob), contract_coords=bool(contract),
+                inject_noise_seed=noise_seed, gain=gain, disparity_at_inf=disp,
+                inject_noise_sigma=sigma)
+
+
+def oracle_render_case(c, dtype=torch.float64):
+    """Run oracle.render on a loaded renderer case; returns outputs and grads (dict)."""
+    from oracle import lightplane_oracle as O
+
+    cfg = renderer_cfg(c)
+    f = lambda t: t.detach().to(dtype=dtype, device="cpu")
+    grid = f(c["grid"]).requires_grad_(True)
+    mlp = f(c["mlp_params"]).requires_grad_(True)
+    enc = f(c["encoding"]).requires_grad_(True)
+    cgrid = f(c["color_grid"]).requires_grad_(True) if "color_grid" in c else None
+    scaffold = f(c["scaffold"]) if "scaffold" in c else None
+    sizes = [[int(v) for v in s] for s in c["grid_sizes"]]
+    color_chn = int(c["color_chn"])
+    outs = O.render(
+        f(c["directions"]), f(c["origins"]), c["grid_idx"].cpu().long(), f(c["near"]), f(c["far"]),
+        enc, grid, sizes, mlp,
+        [int(v) for v in c["n_hidden_trunk"]], [int(v) for v in c["n_hidden_opacity"]],
+        [int(v) for v in c["n_hidden_color"]],
+        scaffold=scaffold, color_grid_flat=cgrid, color_grid_sizes=sizes if cgrid is not None else None,
+        **cfg,
+    )
+    ray_length, nlt, feats = outs[0], outs[1], outs[2][:, :color_chn]
+    loss = (f(c["cot_ray_length"]) * ray_length).sum() + (f(c["cot_nlt"]) * nlt).sum() + (
+        f(c["cot_features"]) * feats).sum()
+    leaves = [grid, mlp, enc] + ([cgrid] if cgrid is not None else [])
+    grads = torch.autograd.grad(loss, leaves)
+    res = dict(ray_length=ray_length, nlt=nlt, features=feats, g_grid=grads[0], g_mlp=grads[1],
+               g_enc=grads[2])
+    if cgrid is not None:
+        res["g_color_grid"] = grads[3]
+    return {k: v.detach() for k, v in res.items()}
+
+
+def splat_cfg(c):
+    num_samples, num_samples_inf, mask_oob, contract = (int(v) for v in c["cfg"])
+    return dict(num_samples=num_samples, num_samples_inf=num_samples_inf,
+                mask_out_of_bounds_samples=bool(mask_oob), contract_coords=bool(contract))
+
+
+def oracle_splat_case(c, dtype=torch.float64):
+    from oracle import lightplane_oracle as O
+
+    f = lambda t: t.detach().to(dtype=dtype, device="cpu")
+    feat = f(c["feature"]).requires_grad_(True)
+    sizes = [[int(v) for v in s] for s in c["out_sizes"]]
+    kw = splat_cfg(c)
+    leaves = [feat]
+    if "mlp_params" in c:
+        mlp = f(c["mlp_params"]).requires_grad_(True)
+        ing = f(c["input_grid"]).requires_grad_(True)
+        kw.update(mlp_params=mlp, mlp_dims=[int(v) for v in c["n_hidden"]], input_grid_flat=ing,
+                  input_sizes=[[int(v) for v in s] for s in c["input_sizes"]])
+        leaves += [mlp, ing]
+    out = O.splat(f(c["directions"]), f(c["origins"]), c["grid_idx"].cpu().long(), f(c["near"]),
+                  f(c["far"]), feat, sizes, **kw)
+    grads = torch.autograd.grad((out * f(c["cot"])).sum(), leaves)
+    res = dict(out=out, g_feat=grads[0])
+    if "mlp_params" in c:
+        res.update(g_mlp=grads[1], g_input_grid=grads[2])
+    return {k: v.detach() for k, v in res.items()}
