@@ -111,17 +111,26 @@ int lp_render_forward(void* stream, const lp_march_cfg* cfg, const lp_decoder_sp
                       int32_t features_stride);
 
 /* Renderer backward.  Replaces `bw_kernel[grid](...)`, lightplane_renderer.py:657-711 /
- * renderer_bw.py:89-627: recomputes the forward in reverse sample order from the saved final
- * negative log transmittance.  grad_grid / grad_color_grid / grad_mlp_params are accumulated
- * into (caller zero-fills); grad_encoding [N, dim_in_color] is fully written. */
+ * renderer_bw.py:89-627.  Like the reference it stores nothing per sample and recomputes the
+ * forward inside the kernel.  Unlike the reference it marches in FORWARD sample order: with
+ * p_j = colour_j . g_feat + t_j * g_len and render weights w_j = T_{j-1} - T_j the opacity
+ * gradient is  dL/d(delta_j*gain*o_j) = T_j p_j - sum_{k>j} w_k p_k + g_nlt,  and the suffix sum is
+ * obtained as (g_feat . features + g_len * ray_length) - sum_{k<=j} w_k p_k from the saved
+ * forward OUTPUTS.  The reference instead walks backwards and unrolls T_j by subtracting from the
+ * saved final NLT (renderer_bw.py:429-433), which loses the low bits whenever later samples carry
+ * huge step lengths (background samples: its Triton path is ~1e-2 off its own naive path there).
+ * Same gradient, better conditioned.
+ *   ray_length [N], features [N, features_stride]: the forward outputs.
+ * grad_grid / grad_color_grid / grad_mlp_params are accumulated into (caller zero-fills);
+ * grad_encoding [N, dim_in_color] is fully written. */
 int lp_render_backward(void* stream, const lp_march_cfg* cfg, const lp_decoder_spec* spec,
                        const lp_rays* rays, const lp_grid_list* grid,
                        const lp_grid_list* color_grid, const lp_grid_list* scaffold,
-                       const float* mlp_params, const float* neg_log_transmittance,
-                       const float* grad_ray_length, const float* grad_neg_log_transmittance,
-                       const float* grad_features, int32_t grad_features_stride,
-                       float* grad_grid, float* grad_color_grid, float* grad_mlp_params,
-                       float* grad_encoding);
+                       const float* mlp_params, const float* ray_length, const float* features,
+                       int32_t features_stride, const float* grad_ray_length,
+                       const float* grad_neg_log_transmittance, const float* grad_features,
+                       int32_t grad_features_stride, float* grad_grid, float* grad_color_grid,
+                       float* grad_mlp_params, float* grad_encoding);
 
 /* Splatter forward.  Replaces BOTH launches of `fw_kernel` (features, then unit weights),
  * lightplane_splatter.py:503-539 / splatter_fw.py:71-165, in one pass: accumulates

@@ -94,7 +94,7 @@ _PROTOTYPES = {
     "lp_render_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32]),
     "lp_render_backward": (
         C.c_int,
-        [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P],
+        [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P],
     ),
     "lp_splat_forward": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "lp_splat_backward": (C.c_int, [_P, _P, _P, _P, _P, _P]),

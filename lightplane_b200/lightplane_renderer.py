@@ -138,8 +138,8 @@ class LightplaneFunction(torch.autograd.Function):
 
     Differentiable inputs: flat feature grid, mlp_params, ray encoding, flat colour grid
     (as in the reference, lightplane_renderer.py:724-756; no gradient w.r.t. ray geometry).
-    Only per-ray tensors are saved for backward -- the backward kernel recomputes every
-    per-sample quantity from the saved final negative log transmittance.
+    Only per-ray tensors are saved for backward (the forward outputs `ray_length`, `features`
+    and the inputs) -- the backward kernel recomputes every per-sample quantity.
     """
 
     @staticmethod
@@ -260,7 +260,6 @@ class LightplaneFunction(torch.autograd.Function):
         ray_length = torch.empty(num_rays, device=device, dtype=torch.float32)
         nlt = torch.empty(num_rays, device=device, dtype=torch.float32)
         features = torch.empty(num_rays, color_chn, device=device, dtype=torch.float32)
-
         if num_rays > 0:
             with torch.cuda.device(device):
                 st = lib.lp_render_forward(
@@ -273,8 +272,8 @@ class LightplaneFunction(torch.autograd.Function):
             _cabi.check(lib, st, "lp_render_forward")
 
         ctx.save_for_backward(
-            nlt, feature_grid_c, mlp_params_c, enc_c, color_c, dirs_c, orig_c, gidx_c, near_c,
-            far_c, scaf_c,
+            ray_length, features, feature_grid_c, mlp_params_c, enc_c, color_c, dirs_c, orig_c,
+            gidx_c, near_c, far_c, scaf_c,
         )
         ctx.lp = (cfg, spec, grid_sizes, color_grid_sizes,
                   None if scaffold is None else list(scaffold.shape) + [1], color_chn)
@@ -283,7 +282,8 @@ class LightplaneFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_ray_length, grad_nlt, grad_features):
         lib = _cabi.get_lib()
-        (nlt, feature_grid, mlp_params, enc, color_grid, dirs, orig, gidx, near, far, scaf) = ctx.saved_tensors
+        (ray_length, features, feature_grid, mlp_params, enc, color_grid, dirs, orig, gidx, near, far,
+         scaf) = ctx.saved_tensors
         cfg, spec, grid_sizes, color_grid_sizes, scaf_size, color_chn = ctx.lp
         device = feature_grid.device
         num_rays = int(dirs.shape[0])
@@ -313,7 +313,7 @@ class LightplaneFunction(torch.autograd.Function):
                     _cabi.stream_ptr(device),
                     _byref(cfg), _byref(spec), _byref(rays_s), _byref(grid_s),
                     _byref(color_s), _byref(scaf_s),
-                    mlp_params.data_ptr(), nlt.data_ptr(),
+                    mlp_params.data_ptr(), ray_length.data_ptr(), features.data_ptr(), color_chn,
                     g_len.data_ptr(), g_nlt.data_ptr(), g_feat.data_ptr(), color_chn,
                     grad_grid.data_ptr(), _cabi.ptr(grad_color), grad_mlp.data_ptr(),
                     grad_enc.data_ptr(),

@@ -1,0 +1,185 @@
+// TEST INFRASTRUCTURE -- SIMT emulation shim.
+//
+// Lets the CUDA sources under lightplane_b200/csrc/ compile with g++ (-DLP_HOSTSIM) so that the
+// kernels' logic (indexing, MLP forward/backward, compositing, atomics, warp collectives) can be
+// debugged against the oracle in the GPU-less build container.  Every CUDA thread of a block is a
+// real OS thread; __syncthreads / warp collectives are barriers.  It is slow (tests use a few
+// hundred rays), it is NOT a CPU fallback: the product library (liblightplane_b200.so) is never
+// built with LP_HOSTSIM and lp_is_device_build() reports which one a .so is.
+#pragma once
+
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct int4 { int x, y, z, w; };
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+#define cudaSuccess 0
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline cudaError_t cudaPeekAtLastError() { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "hostsim"; }
+
+namespace lp_hostsim {
+
+struct WarpCtx {
+  std::barrier<>* bar;
+  uint32_t slots_u[32];
+  int pred[32];
+};
+
+struct BlockCtx {
+  std::barrier<>* bar;
+  unsigned char* smem;
+  std::vector<WarpCtx>* warps;
+};
+
+struct ThreadCtx {
+  uint3 tid, bid;
+  dim3 bdim, gdim;
+  BlockCtx* block;
+  WarpCtx* warp;
+  int lane;
+};
+
+inline thread_local ThreadCtx* g_ctx = nullptr;
+
+template <class F>
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
+  const unsigned nthreads = block.x * block.y * block.z;
+  const unsigned nwarps = (nthreads + 31) / 32;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        std::vector<unsigned char> smem(smem_bytes + 64);
+        std::barrier<> block_bar(nthreads);
+        std::vector<std::unique_ptr<std::barrier<>>> warp_bars;
+        std::vector<WarpCtx> warps(nwarps);
+        for (unsigned w = 0; w < nwarps; ++w) {
+          unsigned cnt = (w + 1) * 32 <= nthreads ? 32 : nthreads - w * 32;
+          warp_bars.emplace_back(new std::barrier<>(cnt));
+          warps[w].bar = warp_bars.back().get();
+        }
+        unsigned char* smem_aligned =
+            reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 63) & ~uintptr_t(63));
+        BlockCtx bctx{&block_bar, smem_aligned, &warps};
+        std::vector<std::thread> threads;
+        threads.reserve(nthreads);
+        for (unsigned t = 0; t < nthreads; ++t) {
+          threads.emplace_back([&, t]() {
+            ThreadCtx ctx;
+            ctx.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+            ctx.bid = uint3{bx, by, bz};
+            ctx.bdim = block;
+            ctx.gdim = grid;
+            ctx.block = &bctx;
+            ctx.warp = &warps[t / 32];
+            ctx.lane = t % 32;
+            g_ctx = &ctx;
+            body();
+            g_ctx = nullptr;
+          });
+        }
+        for (auto& th : threads) th.join();
+      }
+}
+
+inline unsigned char* dyn_smem() { return g_ctx->block->smem; }
+
+}  // namespace lp_hostsim
+
+#define threadIdx (lp_hostsim::g_ctx->tid)
+#define blockIdx (lp_hostsim::g_ctx->bid)
+#define blockDim (lp_hostsim::g_ctx->bdim)
+#define gridDim (lp_hostsim::g_ctx->gdim)
+
+#define LP_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(lp_hostsim::dyn_smem())
+#define LP_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  lp_hostsim::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+
+static inline void __syncthreads() { lp_hostsim::g_ctx->block->bar->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { lp_hostsim::g_ctx->warp->bar->arrive_and_wait(); }
+
+template <class T>
+static inline T lp_hs_exchange(T v, int src_lane) {
+  static_assert(sizeof(T) == 4, "32-bit shuffles only");
+  auto* w = lp_hostsim::g_ctx->warp;
+  uint32_t bits;
+  std::memcpy(&bits, &v, 4);
+  w->slots_u[lp_hostsim::g_ctx->lane] = bits;
+  w->bar->arrive_and_wait();
+  uint32_t got = w->slots_u[src_lane & 31];
+  w->bar->arrive_and_wait();
+  T out;
+  std::memcpy(&out, &got, 4);
+  return out;
+}
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return lp_hs_exchange(v, src); }
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) {
+  return lp_hs_exchange(v, lp_hostsim::g_ctx->lane ^ m);
+}
+template <class T>
+static inline T __shfl_down_sync(unsigned, T v, int d, int = 32) {
+  int l = lp_hostsim::g_ctx->lane + d;
+  return lp_hs_exchange(v, l > 31 ? lp_hostsim::g_ctx->lane : l);
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  auto* w = lp_hostsim::g_ctx->warp;
+  w->pred[lp_hostsim::g_ctx->lane] = pred ? 1 : 0;
+  w->bar->arrive_and_wait();
+  unsigned m = 0;
+  for (int i = 0; i < 32; ++i) m |= (w->pred[i] ? 1u : 0u) << i;
+  w->bar->arrive_and_wait();
+  return m;
+}
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
+
+static inline float atomicAdd(float* p, float v) {
+  return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed);
+}
+static inline int atomicAdd(int* p, int v) {
+  return std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_relaxed);
+}
+
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+// (glibc already declares __expf/__logf; kernels use expf/logf)
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline long long min(long long a, long long b) { return a < b ? a : b; }
+static inline long long max(long long a, long long b) { return a > b ? a : b; }
+static inline float __fdividef(float a, float b) { return a / b; }
+static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
+static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }

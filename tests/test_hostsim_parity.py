@@ -1,0 +1,42 @@
+"""GPU-less debugging aid: the CUDA kernel sources compiled for the host against the SIMT
+emulation shim (tests/hostsim/) are run on the golden cases and compared with the reference's
+outputs.  This exercises kernel LOGIC only; the parity tests proper are the `-m gpu` tests."""
+import os
+import subprocess
+
+import pytest
+import torch
+
+from _golden import case_names, load_case, rel_err
+from _lowlevel import render_case, splat_case
+from lightplane_b200 import _cabi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "hostsim", "liblp_hostsim.so")
+CSRC = os.path.join(os.path.dirname(HERE), "lightplane_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.run(["make", "-s", "-C", CSRC, "hostsim"], check=True)
+    lib = _cabi.load_library(LIB)
+    assert lib.lp_is_device_build() == 0
+    return lib
+
+
+@pytest.mark.parametrize("name", case_names("render_"))
+def test_hostsim_renderer(lib, name):
+    c = load_case(name)
+    got = render_case(lib, c, "cpu")
+    for k, v in got.items():
+        assert torch.isfinite(v).all(), (name, k)
+        assert rel_err(v, c["naive_" + k]) < 2e-4, (name, k, rel_err(v, c["naive_" + k]))
+
+
+@pytest.mark.parametrize("name", case_names("splat_"))
+def test_hostsim_splatter(lib, name):
+    c = load_case(name)
+    got = splat_case(lib, c, "cpu")
+    for k, v in got.items():
+        assert torch.isfinite(v).all(), (name, k)
+        assert rel_err(v, c["naive_" + k]) < 2e-4, (name, k, rel_err(v, c["naive_" + k]))
