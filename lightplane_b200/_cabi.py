@@ -225,3 +225,37 @@ def stream_ptr(device: torch.device) -> Optional[int]:
 def byref(s: Optional[C.Structure]):
     """Pointer to a ctypes struct as c_void_p (None -> NULL)."""
     return None if s is None else C.cast(C.pointer(s), C.c_void_p)
+
+
+# ------------------------------------------------------------------------------------------
+# optional per-launch device timing (used by bench.py for the roofline numbers)
+# ------------------------------------------------------------------------------------------
+_PROFILE: Optional[list] = None
+
+
+def profile_begin() -> None:
+    """Start recording a CUDA-event pair around every C-ABI launch."""
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_end():
+    """Stop recording; returns `[(entry_point, milliseconds), ...]` (synchronises)."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE or [], None
+    torch.cuda.synchronize()
+    return [(name, a.elapsed_time(b)) for name, a, b in rec]
+
+
+def call(lib, name: str, *args) -> int:
+    """Invoke C-ABI entry point `name`; when profiling is on, bracket it with CUDA events recorded
+    on the current stream (the one the launch goes to)."""
+    fn = getattr(lib, name)
+    if _PROFILE is None:
+        return fn(*args)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    st = fn(*args)
+    b.record()
+    _PROFILE.append((name, a, b))
+    return st

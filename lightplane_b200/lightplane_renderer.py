@@ -262,7 +262,7 @@ class LightplaneFunction(torch.autograd.Function):
         features = torch.empty(num_rays, color_chn, device=device, dtype=torch.float32)
         if num_rays > 0:
             with torch.cuda.device(device):
-                st = lib.lp_render_forward(
+                st = _cabi.call(lib, "lp_render_forward",
                     _cabi.stream_ptr(device),
                     _byref(cfg), _byref(spec), _byref(rays_s), _byref(grid_s),
                     _byref(color_s), _byref(scaf_s),
@@ -309,7 +309,7 @@ class LightplaneFunction(torch.autograd.Function):
 
         if num_rays > 0:
             with torch.cuda.device(device):
-                st = lib.lp_render_backward(
+                st = _cabi.call(lib, "lp_render_backward",
                     _cabi.stream_ptr(device),
                     _byref(cfg), _byref(spec), _byref(rays_s), _byref(grid_s),
                     _byref(color_s), _byref(scaf_s),

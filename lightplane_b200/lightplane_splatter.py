@@ -42,11 +42,16 @@ def lightplane_splatter(
     regenerate_code: bool = False,
     triton_block_size: int = 16,
     triton_num_warps: int = 4,
+    process_group=None,
 ):
     """Splat `rays.encoding` into a zero-initialised grid-list of shapes `output_grid_size`
     at every sample of the ray march and normalise by the accumulated interpolation weights
     (reference semantics: lightplane_splatter.py:45-129).  Returns a list of `[B,D,H,W,C]`
-    grids, or the flat `[sum BDHW, C]` tensor when `return_list=False`."""
+    grids, or the flat `[sum BDHW, C]` tensor when `return_list=False`.
+
+    `process_group` (extension, not in the reference): when rays are sharded across ranks, pass
+    the `torch.distributed` group; the un-normalised feature and weight grids are then
+    SUM-all-reduced before the normalisation, so every rank returns the full result."""
     del regenerate_code, triton_block_size, triton_num_warps
     sizes = _sizes_list(output_grid_size)
     out = LightplaneSplatterFunction.apply(
@@ -54,7 +59,7 @@ def lightplane_splatter(
         sizes, None, None,
         rays.directions, rays.origins, rays.grid_idx, rays.near, rays.far,
         int(num_samples), int(num_samples_inf), bool(mask_out_of_bounds_samples),
-        bool(contract_coords), float(disparity_at_inf),
+        bool(contract_coords), float(disparity_at_inf), process_group,
     )
     return list(unflatten_grid(out, sizes)) if return_list else out
 
@@ -75,6 +80,7 @@ def lightplane_mlp_splatter(
     regenerate_code: bool = False,
     triton_block_size: int = 16,
     triton_num_warps: int = 4,
+    process_group=None,
 ):
     """`input_grid -> sample -> + rays.encoding -> MLP -> splat -> output grid`
     (reference semantics: lightplane_splatter.py:184-288)."""
@@ -90,7 +96,7 @@ def lightplane_mlp_splatter(
         sizes, input_sizes, n_hidden,
         rays.directions, rays.origins, rays.grid_idx, rays.near, rays.far,
         int(num_samples), int(num_samples_inf), bool(mask_out_of_bounds_samples),
-        bool(contract_coords), float(disparity_at_inf),
+        bool(contract_coords), float(disparity_at_inf), process_group,
     )
     return list(unflatten_grid(out, sizes)) if return_list else out
 
@@ -115,6 +121,7 @@ class LightplaneSplatterFunction(torch.autograd.Function):
         mask_out_of_bounds_samples: bool,
         contract_coords: bool,
         disparity_at_inf: float,
+        process_group=None,
     ):
         lib = _cabi.get_lib()
         device = directions.device
@@ -166,17 +173,22 @@ class LightplaneSplatterFunction(torch.autograd.Function):
         with torch.cuda.device(device):
             if num_rays > 0:
                 if use_mlp:
-                    st = lib.lp_mlp_splat_forward(
+                    st = _cabi.call(lib, "lp_mlp_splat_forward",
                         stream, _byref(cfg), _byref(spec), _byref(rays_s), None, _byref(in_s),
                         mlp_c.data_ptr(), _byref(out_s), weight_grid.data_ptr(),
                     )
                     _cabi.check(lib, st, "lp_mlp_splat_forward")
                 else:
-                    st = lib.lp_splat_forward(
+                    st = _cabi.call(lib, "lp_splat_forward",
                         stream, _byref(cfg), _byref(rays_s), None, _byref(out_s),
                         weight_grid.data_ptr(),
                     )
                     _cabi.check(lib, st, "lp_splat_forward")
+            if process_group is not None:
+                # ray-sharded splatting: reduce the UN-normalised accumulators (distributed.py)
+                from .distributed import all_reduce_sum_
+
+                all_reduce_sum_([feature_grid, weight_grid], process_group)
             st = lib.lp_splat_normalize(
                 stream, feature_grid.data_ptr(), weight_grid.data_ptr(), rows, chn_out
             )
@@ -208,17 +220,17 @@ class LightplaneSplatterFunction(torch.autograd.Function):
             with torch.cuda.device(device):
                 if use_mlp:
                     in_s = _cabi.make_grid_list(input_grid, input_sizes)
-                    st = lib.lp_mlp_splat_backward(
+                    st = _cabi.call(lib, "lp_mlp_splat_backward",
                         stream, _byref(cfg), _byref(spec), _byref(rays_s), None, _byref(in_s),
                         mlp_params.data_ptr(), _byref(g_s), grad_feat.data_ptr(),
                         grad_mlp.data_ptr(), grad_in.data_ptr(),
                     )
                     _cabi.check(lib, st, "lp_mlp_splat_backward")
                 else:
-                    st = lib.lp_splat_backward(
+                    st = _cabi.call(lib, "lp_splat_backward",
                         stream, _byref(cfg), _byref(rays_s), None, _byref(g_s), grad_feat.data_ptr()
                     )
                     _cabi.check(lib, st, "lp_splat_backward")
         else:
             grad_feat.zero_()
-        return (grad_feat, grad_mlp, grad_in) + (None,) * 13
+        return (grad_feat, grad_mlp, grad_in) + (None,) * 14
