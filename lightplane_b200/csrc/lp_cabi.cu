@@ -7,9 +7,7 @@
 #include "lp_common.cuh"
 #include "lp_render_generic.cuh"
 #include "lp_splat.cuh"
-#ifndef LP_HOSTSIM
 #include "lp_render_fast.cuh"
-#endif
 
 static thread_local char g_err[512] = "";
 
@@ -228,11 +226,12 @@ int lp_render_forward(void* stream, const lp_march_cfg* cfg, const lp_decoder_sp
     LP_FAIL(LP_ERR_INVALID_ARG, "an output pointer is NULL");
   if (features_stride < a.D.n_feat) LP_FAIL(LP_ERR_INVALID_ARG, "features_stride < num_color_used");
   cudaStream_t st = (cudaStream_t)stream;
-#ifndef LP_HOSTSIM
-  if (lp_fast_render_supported(a))
-    return lp_fast_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance,
-                                  out_features, features_stride);
-#endif
+  if (lp_fast_render_supported(a)) {
+    if ((rc = lp_fast_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance,
+                                     out_features, features_stride)))
+      LP_FAIL(rc, "fast forward launch setup failed");
+    return lp_check_launch("lp_render_forward(fast)");
+  }
   const int pf = (a.D.n_params + 3) & ~3;
   const int per_warp = (a.A.total + a.D.in_c + a.D.n_feat) * LP_LS;
   int warps, pin; size_t bytes;
@@ -269,9 +268,10 @@ int lp_render_backward(void* stream, const lp_march_cfg* cfg, const lp_decoder_s
   io.g_len = grad_ray_length; io.g_nlt = grad_neg_log_transmittance; io.g_feat = grad_features;
   io.g_feat_stride = grad_features_stride;
   io.g_grid = grad_grid; io.g_cgrid = grad_color_grid; io.g_params = grad_mlp_params; io.g_enc = grad_encoding;
-#ifndef LP_HOSTSIM
-  if (lp_fast_render_supported(a)) return lp_fast_render_backward(st, a, mlp_params, io);
-#endif
+  if (lp_fast_render_supported(a) && lp_fast_render_backward_supported(a)) {
+    if ((rc = lp_fast_render_backward(st, a, mlp_params, io))) LP_FAIL(rc, "fast backward launch setup failed");
+    return lp_check_launch("lp_render_backward(fast)");
+  }
   const int pf = (a.D.n_params + 3) & ~3;
   const int per_warp = (a.A.total + 3 * a.D.max_dim + 2 * a.D.in_c + a.D.n_feat) * LP_LS;
   int warps, pin; size_t bytes;

@@ -47,3 +47,34 @@ LP_DEVICE float4 lp_ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 #endif
 }
+
+// ---------------------------------------------------------------------------------------------
+// warp-level tensor-core primitives (mma.sync m16n8k8, TF32 in / FP32 accumulate)
+// Fragment layout (lane = 4*g + t): A 16x8 row-major: a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4);
+// B 8x8: b0=(k=t,n=g) b1=(k=t+4,n=g); C 16x8: c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1).
+// ---------------------------------------------------------------------------------------------
+LP_DEVICE float lp_tf32_rna(float x) {  // round-to-nearest TF32 (10-bit mantissa), as fp32 bits
+#if defined(LP_HOSTSIM)
+  unsigned u = __float_as_uint(x);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u += 0x00001000u;  // round half away from zero on the magnitude, like cvt.rna
+  u &= 0xffffe000u;
+  return __uint_as_float(u);
+#else
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+#endif
+}
+
+LP_DEVICE void lp_mma_tf32(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
+#if defined(LP_HOSTSIM)
+  lp_hostsim_mma_m16n8k8(d, a, b);
+#else
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
+        "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
+#endif
+}

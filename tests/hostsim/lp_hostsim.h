@@ -51,6 +51,9 @@ struct WarpCtx {
   std::barrier<>* bar;
   uint32_t slots_u[32];
   int pred[32];
+  float mma_a[32 * 4];
+  float mma_b[32 * 2];
+  void* mma;
 };
 
 struct BlockCtx {
@@ -183,3 +186,34 @@ static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); ret
 static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
 static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
+
+// mma.sync.m16n8k8 TF32 emulation: every lane publishes its fragments, then computes its own four
+// outputs from the assembled 16x8 / 8x8 operands.  Operands are truncated to TF32 (19 bits) the
+// way the tensor core reads them, so precision tests are meaningful here too.
+static inline float lp_hs_trunc_tf32(float x) {
+  unsigned u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; float y; std::memcpy(&y, &u, 4); return y;
+}
+static inline void lp_hostsim_mma_m16n8k8(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
+  auto* w = lp_hostsim::g_ctx->warp;
+  const int lane = lp_hostsim::g_ctx->lane;
+  float (*A)[4] = reinterpret_cast<float (*)[4]>(w->mma_a);
+  float (*B)[2] = reinterpret_cast<float (*)[2]>(w->mma_b);
+  for (int i = 0; i < 4; ++i) A[lane][i] = lp_hs_trunc_tf32(a[i]);
+  for (int i = 0; i < 2; ++i) B[lane][i] = lp_hs_trunc_tf32(b[i]);
+  w->bar->arrive_and_wait();
+  const int g = lane >> 2, t = lane & 3;
+  auto Aat = [&](int row, int k) -> float {  // row 0..15, k 0..7
+    int gg = row & 7, hi_row = row >> 3, tt = k & 3, hi_k = k >> 2;
+    return A[gg * 4 + tt][hi_row + 2 * hi_k];
+  };
+  auto Bat = [&](int k, int n) -> float { return B[n * 4 + (k & 3)][k >> 2]; };
+  float out[4];
+  for (int i = 0; i < 4; ++i) {
+    int row = g + 8 * (i >> 1), col = 2 * t + (i & 1);
+    float acc = d[i];
+    for (int k = 0; k < 8; ++k) acc += Aat(row, k) * Bat(k, col);
+    out[i] = acc;
+  }
+  w->bar->arrive_and_wait();
+  for (int i = 0; i < 4; ++i) d[i] = out[i];
+}
