@@ -150,6 +150,8 @@ LP_DEVICE void lp_init_bias(float (&acc)[2][4][4], const float* bias, int t) {
 }
 
 // One 3xTF32 dense layer for both m-tiles: acc[mt][n] += A[mt] * W, A given in A-fragment order.
+// The three products of one accumulator are dependent; they are issued product-major so that
+// eight independent accumulators separate two dependent mma instructions.
 template <int KSTEPS>
 LP_DEVICE void lp_layer3x(const float* Wf, float (&acc)[2][4][4], const float (&ain)[2][KSTEPS][4], int lane) {
 #pragma unroll
@@ -159,17 +161,24 @@ LP_DEVICE void lp_layer3x(const float* Wf, float (&acc)[2][4][4], const float (&
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) { ahi[mt][i] = lp_tf32_rna(ain[mt][j][i]); alo[mt][i] = ain[mt][j][i] - ahi[mt][i]; }
+    float bh[4][2], bl[4][2];
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       const float4 w = *reinterpret_cast<const float4*>(Wf + ((j * 4 + n) * 32 + lane) * 4);
-      const float bh[2] = {w.x, w.y}, bl[2] = {w.z, w.w};
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        lp_mma_tf32(acc[mt][n], alo[mt], bh);
-        lp_mma_tf32(acc[mt][n], ahi[mt], bl);
-        lp_mma_tf32(acc[mt][n], ahi[mt], bh);
-      }
+      bh[n][0] = w.x; bh[n][1] = w.y; bl[n][0] = w.z; bl[n][1] = w.w;
     }
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) lp_mma_tf32(acc[mt][n], alo[mt], bh[n]);
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) lp_mma_tf32(acc[mt][n], ahi[mt], bl[n]);
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) lp_mma_tf32(acc[mt][n], ahi[mt], bh[n]);
   }
 }
 
@@ -376,6 +385,477 @@ __global__ void __launch_bounds__(256) lp_render_fwd_fast_kernel(LpRays R, LpMar
   }
 }
 
+
+// ===========================================================================================
+// backward
+// ===========================================================================================
+// Shared-memory tiles of one warp (32 samples), all [sample][feature] with an XOR swizzle of the
+// feature index by 8*(sample&3) so that both the C-fragment stores (float2 per lane) and the
+// transposed fragment loads of the dW products are bank-conflict free without padding.
+LP_DEVICE int lp_sw32(int s, int f) { return s * 32 + (f ^ ((s & 3) << 3)); }
+LP_DEVICE int lp_sw16(int s, int f) { return s * 16 + (f ^ (((s >> 1) & 1) << 3)); }
+
+// store an activation given in A-fragment order (see lp_relu_to_a) as TF32 into a 32-wide tile
+LP_DEVICE void lp_store_tile_a(float* tile, const float (&a)[2][4][4], int g, int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      *reinterpret_cast<float2*>(tile + lp_sw32(16 * mt + g, 8 * n + 2 * t)) =
+          make_float2(lp_tf32_rna(a[mt][n][0]), lp_tf32_rna(a[mt][n][2]));
+      *reinterpret_cast<float2*>(tile + lp_sw32(16 * mt + 8 + g, 8 * n + 2 * t)) =
+          make_float2(lp_tf32_rna(a[mt][n][1]), lp_tf32_rna(a[mt][n][3]));
+    }
+}
+// same for a gradient held in C-fragment order
+LP_DEVICE void lp_store_tile_c(float* tile, const float (&c)[2][4][4], int g, int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      *reinterpret_cast<float2*>(tile + lp_sw32(16 * mt + g, 8 * n + 2 * t)) =
+          make_float2(lp_tf32_rna(c[mt][n][0]), lp_tf32_rna(c[mt][n][1]));
+      *reinterpret_cast<float2*>(tile + lp_sw32(16 * mt + 8 + g, 8 * n + 2 * t)) =
+          make_float2(lp_tf32_rna(c[mt][n][2]), lp_tf32_rna(c[mt][n][3]));
+    }
+}
+
+// ReLU mask of an activation in A-fragment order: bit (mt*16 + n*4 + i) set iff a[mt][n][i] > 0
+LP_DEVICE unsigned lp_mask_a(const float (&a)[2][4][4]) {
+  unsigned m = 0;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m |= (a[mt][n][i] > 0.f ? 1u : 0u) << (mt * 16 + n * 4 + i);
+  return m;
+}
+// gate a gradient in C-fragment order by a mask recorded in A-fragment order (i: a1<->c2, a2<->c1)
+LP_DEVICE void lp_gate_c(float (&c)[2][4][4], unsigned mask) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const unsigned b = mask >> (mt * 16 + n * 4);
+      if (!(b & 1u)) c[mt][n][0] = 0.f;
+      if (!(b & 4u)) c[mt][n][1] = 0.f;
+      if (!(b & 2u)) c[mt][n][2] = 0.f;
+      if (!(b & 8u)) c[mt][n][3] = 0.f;
+    }
+}
+// C-fragment gradient -> TF32 A-fragments of the dX product
+LP_DEVICE void lp_c_to_a_tf32(const float (&c)[2][4][4], float (&a)[2][4][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      a[mt][n][0] = lp_tf32_rna(c[mt][n][0]);
+      a[mt][n][1] = lp_tf32_rna(c[mt][n][2]);
+      a[mt][n][2] = lp_tf32_rna(c[mt][n][1]);
+      a[mt][n][3] = lp_tf32_rna(c[mt][n][3]);
+    }
+}
+
+// dX: acc[mt][nn] += A[mt][jk] * B(jk, nn), B-fragments {hi0, hi1} from the dX weight image
+template <int NN, int KS>
+LP_DEVICE void lp_dx(const float* Xf, float (&acc)[2][NN][4], const float (&a)[2][KS][4], int lane) {
+#pragma unroll
+  for (int jk = 0; jk < KS; ++jk)
+#pragma unroll
+    for (int nn = 0; nn < NN; ++nn) {
+      const float2 w = *reinterpret_cast<const float2*>(Xf + ((jk * NN + nn) * 32 + lane) * 2);
+      const float b[2] = {w.x, w.y};
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) lp_mma_tf32(acc[mt][nn], a[mt][jk], b);
+    }
+}
+
+// dW tile update over the warp's 32 samples:  acc[mf][nn] += X^T(features 16mf.., samples) * dY
+// X tile [32][KF] (swizzled), dY tile [32][NO*8]; accumulators live in smem in fragment order.
+template <int KF, int NO>
+LP_DEVICE void lp_dw(float* accum, const float* X, const float* dY, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  constexpr int MF = KF / 16;
+  float c[MF][NO][4];
+#pragma unroll
+  for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+    for (int nn = 0; nn < NO; ++nn) {
+      const float4 v = *reinterpret_cast<const float4*>(accum + ((mf * NO + nn) * 32 + lane) * 4);
+      c[mf][nn][0] = v.x; c[mf][nn][1] = v.y; c[mf][nn][2] = v.z; c[mf][nn][3] = v.w;
+    }
+#pragma unroll
+  for (int js = 0; js < 4; ++js) {
+    float a[MF][4];
+#pragma unroll
+    for (int mf = 0; mf < MF; ++mf) {
+      if (KF == 16) {
+        a[mf][0] = X[lp_sw16(8 * js + t, g)];     a[mf][1] = X[lp_sw16(8 * js + t, g + 8)];
+        a[mf][2] = X[lp_sw16(8 * js + t + 4, g)]; a[mf][3] = X[lp_sw16(8 * js + t + 4, g + 8)];
+      } else {
+        a[mf][0] = X[lp_sw32(8 * js + t, 16 * mf + g)];     a[mf][1] = X[lp_sw32(8 * js + t, 16 * mf + g + 8)];
+        a[mf][2] = X[lp_sw32(8 * js + t + 4, 16 * mf + g)]; a[mf][3] = X[lp_sw32(8 * js + t + 4, 16 * mf + g + 8)];
+      }
+    }
+#pragma unroll
+    for (int nn = 0; nn < NO; ++nn) {
+      const float b[2] = {dY[lp_sw32(8 * js + t, 8 * nn + g)], dY[lp_sw32(8 * js + t + 4, 8 * nn + g)]};
+#pragma unroll
+      for (int mf = 0; mf < MF; ++mf) lp_mma_tf32(c[mf][nn], a[mf], b);
+    }
+  }
+#pragma unroll
+  for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+    for (int nn = 0; nn < NO; ++nn)
+      *reinterpret_cast<float4*>(accum + ((mf * NO + nn) * 32 + lane) * 4) =
+          make_float4(c[mf][nn][0], c[mf][nn][1], c[mf][nn][2], c[mf][nn][3]);
+}
+
+// bias gradient: lane n accumulates the column sum of the dY tile
+LP_DEVICE float lp_colsum(const float* dY, int lane) {
+  float s = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) s += dY[lp_sw32(r, lane)];
+  return s;
+}
+
+// scatter one row's channel chunk(s) of d_x0 into the grid gradient
+template <int C>
+LP_DEVICE void lp_splat_row(const LpGridSet& G, float* grad, int b, float x, float y, float z, float oob, int t,
+                            const float (&d)[C / 4]) {
+  if (oob == 0.f) return;
+  for (int gi = 0; gi < G.n; ++gi) {
+    long long off[8];
+    float w[8];
+    const int nt = lp_taps(G.g[gi], C, b, x, y, z, off, w);
+#pragma unroll
+    for (int tp = 0; tp < 8; ++tp) {
+      if (tp < nt && w[tp] != 0.f) {
+        const float ww = w[tp] * oob;
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k)
+          lp_red_add4(grad + off[tp] + 16 * k + 4 * t, ww * d[4 * k], ww * d[4 * k + 1], ww * d[4 * k + 2],
+                      ww * d[4 * k + 3]);
+      }
+    }
+  }
+}
+
+// per-warp shared-memory map of the backward kernel (floats)
+template <int C>
+struct BLay {
+  static constexpr int X0 = 0;                 // [32][C]
+  static constexpr int H1 = X0 + 32 * C;       // [32][32] each
+  static constexpr int TR = H1 + 1024;
+  static constexpr int XC = TR + 1024;
+  static constexpr int HO = XC + 1024;
+  static constexpr int HC = HO + 1024;
+  static constexpr int DY = HC + 1024;         // gradient tile (B operand of dW, bias sums)
+  static constexpr int AW_T0 = DY + 1024;      // dW accumulators, fragment order [mf][nn][32][4]
+  static constexpr int AW_T1 = AW_T0 + C * 32;
+  static constexpr int AW_O0 = AW_T1 + 1024;
+  static constexpr int AW_C0 = AW_O0 + 1024;
+  static constexpr int AW_LC = AW_C0 + 1024;   // hc^T * dY_last [2][1][32][4]
+  static constexpr int AW_LO = AW_LC + 256;    // ho^T * dY_last
+  static constexpr int RAYS = AW_LO + 256;     // per ray: total, g_nlt, g_len  [3][32]
+  static constexpr int END = RAYS + 96;
+};
+
+template <int C>
+__global__ void __launch_bounds__(128) lp_render_bwd_fast_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
+                                                                const float* __restrict__ params, LpBwdIo io) {
+  using L = Lay<C>;
+  using B = BLay<C>;
+  LP_DYN_SMEM(float, smem);
+  lp_build_weights<C, true>(smem, params, D);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  float* ws = smem + L::END + warp * B::END;
+  for (int e = lane; e < B::RAYS - B::AW_T0; e += 32) ws[B::AW_T0 + e] = 0.f;
+  float db[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // bias gradients: lane n owns column n (t0,t1,o0,c0,last)
+  __syncthreads();
+  const float* bias = smem + L::BIAS;
+  const int num_tiles = (R.n + 31) / 32;
+  const int tot = M.S + M.S_inf;
+
+  for (int tile = blockIdx.x * nwarps + warp; tile < num_tiles; tile += gridDim.x * nwarps) {
+    const int rbase = tile * 32;
+    Rows r;
+    lp_load_rows(R, rbase, g, G.g[0].B, r);
+    __syncwarp();
+    {  // per-ray constants computed by the lane that owns the ray
+      const int ray = rbase + lane;
+      const bool act = ray < R.n;
+      const int q = act ? ray : R.n - 1;
+      float gl = act ? io.g_len[q] : 0.f, gn = act ? io.g_nlt[q] : 0.f;
+      float tot_ = gl * io.len[q];
+      for (int c = 0; c < D.n_feat; ++c)
+        tot_ = fmaf(act ? io.g_feat[(long long)q * io.g_feat_stride + c] : 0.f, io.feat[(long long)q * io.feat_stride + c], tot_);
+      ws[B::RAYS + lane] = tot_; ws[B::RAYS + 32 + lane] = gn; ws[B::RAYS + 64 + lane] = gl;
+    }
+    __syncwarp();
+    float nlt[4] = {0.f, 0.f, 0.f, 0.f}, T[4] = {1.f, 1.f, 1.f, 1.f}, prefix[4] = {0.f, 0.f, 0.f, 0.f}, gF[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      gF[i] = (r.active[i] && t < D.n_feat) ? io.g_feat[(long long)r.ray[i] * io.g_feat_stride + t] : 0.f;
+    float genc[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) genc[mt][n][i] = 0.f;
+
+    for (int step = 0; step < tot; ++step) {
+      // ------------------------------ forward recompute ------------------------------
+      float depth[4], delta[4];
+      unsigned m_h1, m_tr, m_ho, m_hc;
+      float last[2][4];
+      {
+        float xa[4][C / 4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const SamplePos p = lp_sample_pos(r, i, step, M);
+          depth[i] = p.depth; delta[i] = p.delta;
+          lp_gather_row<C>(G, r.b[i], p.x, p.y, p.z, p.oob, t, xa[i]);
+          const int s = 16 * (i >> 1) + 8 * (i & 1) + g;
+#pragma unroll
+          for (int k = 0; k < C / 16; ++k) {
+            const float4 v = make_float4(lp_tf32_rna(xa[i][4 * k]), lp_tf32_rna(xa[i][4 * k + 1]),
+                                         lp_tf32_rna(xa[i][4 * k + 2]), lp_tf32_rna(xa[i][4 * k + 3]));
+            if (C == 16) *reinterpret_cast<float4*>(ws + B::X0 + lp_sw16(s, 4 * t)) = v;
+            else *reinterpret_cast<float4*>(ws + B::X0 + lp_sw32(s, 16 * k + 4 * t)) = v;
+          }
+        }
+        float acc[2][4][4], a[2][4][4], tr[2][4][4];
+        {
+          float a0[2][C / 8][4];
+          lp_x0_to_a<C>(xa, a0);
+          lp_init_bias(acc, bias, t);
+          lp_layer3x<C / 8>(smem + L::F_T0, acc, a0, lane);
+        }
+        lp_relu_to_a(acc, a);
+        m_h1 = lp_mask_a(a);
+        lp_store_tile_a(ws + B::H1, a, g, t);
+        lp_init_bias(acc, bias + 32, t);
+        lp_layer3x<4>(smem + L::F_T1, acc, a, lane);
+        lp_relu_to_a(acc, tr);
+        m_tr = lp_mask_a(tr);
+        lp_store_tile_a(ws + B::TR, tr, g, t);
+        lp_init_bias(acc, bias + 64, t);
+        lp_layer3x<4>(smem + L::F_O0, acc, tr, lane);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) { last[mt][0] = last[mt][2] = bias[128 + 2 * t]; last[mt][1] = last[mt][3] = bias[128 + 2 * t + 1]; }
+        lp_relu_to_a(acc, a);
+        m_ho = lp_mask_a(a);
+        lp_store_tile_a(ws + B::HO, a, g, t);
+        lp_layer3x_n1(smem + L::F_LO, last, a, lane);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const int q0 = r.active[2 * mt] ? r.ray[2 * mt] : R.n - 1, q1 = r.active[2 * mt + 1] ? r.ray[2 * mt + 1] : R.n - 1;
+            const float2 e0 = __ldg(reinterpret_cast<const float2*>(R.enc + (long long)q0 * H + 8 * n + 2 * t));
+            const float2 e1 = __ldg(reinterpret_cast<const float2*>(R.enc + (long long)q1 * H + 8 * n + 2 * t));
+            tr[mt][n][0] += e0.x; tr[mt][n][2] += e0.y; tr[mt][n][1] += e1.x; tr[mt][n][3] += e1.y;
+          }
+        lp_store_tile_a(ws + B::XC, tr, g, t);
+        lp_init_bias(acc, bias + 96, t);
+        lp_layer3x<4>(smem + L::F_C0, acc, tr, lane);
+        lp_relu_to_a(acc, a);
+        m_hc = lp_mask_a(a);
+        lp_store_tile_a(ws + B::HC, a, g, t);
+        lp_layer3x_n1(smem + L::F_LC, last, a, lane);
+      }
+      // ------------------------------ compositing gradient ------------------------------
+      float dl[2][4];  // dY of the last layer in C-fragment order: cols (2t: d_logc_t, 2t+1: g_raw)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int mt = i >> 1, h = i & 1, s = 16 * mt + 8 * h + g;
+        float raw = last[mt][2 * h + 1];
+        if (M.noise) raw += M.sigma * lp_sample_noise(M, r.ray[i], step);
+        nlt[i] += delta[i] * M.gain * lp_softplus(raw);
+        const float Tn = expf(-nlt[i]);
+        const float w = T[i] - Tn;
+        T[i] = Tn;
+        const float sg = lp_sigmoid(last[mt][2 * h]);
+        float pc = (t < D.n_feat) ? sg * gF[i] : 0.f;  // this lane's colour channel
+        pc += __shfl_xor_sync(LP_FULL_MASK, pc, 1);
+        pc += __shfl_xor_sync(LP_FULL_MASK, pc, 2);
+        const float p = fmaf(depth[i], ws[B::RAYS + 64 + s], pc);
+        prefix[i] = fmaf(w, p, prefix[i]);
+        const float suffix = (step == tot - 1) ? 0.f : ws[B::RAYS + s] - prefix[i];
+        const float g_dop = Tn * p - suffix + ws[B::RAYS + 32 + s];
+        dl[mt][2 * h + 1] = g_dop * delta[i] * M.gain * lp_sigmoid(raw);
+        dl[mt][2 * h] = (t < D.n_feat) ? w * gF[i] * sg * (1.f - sg) : 0.f;
+      }
+      // ------------------------------ backward sweep ------------------------------
+      float d1[2][4][4], d2[2][4][4], a[2][4][4];
+      // last layer: dW (hc^T dY, ho^T dY), db, and d_hc / d_ho
+      {
+        __syncwarp();
+        // dY_last tile: 8 valid columns (cols 8..31 of the tile are not read by the NO=1 product)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          *reinterpret_cast<float2*>(ws + B::DY + lp_sw32(16 * mt + g, 2 * t)) = make_float2(lp_tf32_rna(dl[mt][0]), lp_tf32_rna(dl[mt][1]));
+          *reinterpret_cast<float2*>(ws + B::DY + lp_sw32(16 * mt + 8 + g, 2 * t)) = make_float2(lp_tf32_rna(dl[mt][2]), lp_tf32_rna(dl[mt][3]));
+        }
+        __syncwarp();
+        lp_dw<32, 1>(ws + B::AW_LC, ws + B::HC, ws + B::DY, lane);
+        lp_dw<32, 1>(ws + B::AW_LO, ws + B::HO, ws + B::DY, lane);
+        if (lane < 8) {
+          float sacc = 0.f;
+          for (int rr = 0; rr < 32; ++rr) sacc += ws[B::DY + lp_sw32(rr, lane)];
+          db[4] += sacc;
+        }
+        float al[2][1][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          al[mt][0][0] = lp_tf32_rna(dl[mt][0]); al[mt][0][1] = lp_tf32_rna(dl[mt][2]);
+          al[mt][0][2] = lp_tf32_rna(dl[mt][1]); al[mt][0][3] = lp_tf32_rna(dl[mt][3]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { d1[mt][n][i] = 0.f; d2[mt][n][i] = 0.f; }
+        lp_dx<4, 1>(smem + L::X_LC, d1, al, lane);  // d_hc
+        lp_dx<4, 1>(smem + L::X_LO, d2, al, lane);  // d_ho
+      }
+      lp_gate_c(d1, m_hc);
+      lp_gate_c(d2, m_ho);
+      // colour hidden layer: dW_c0 += xc^T d_hc', d_xc = d_hc' Wc0^T
+      __syncwarp();
+      lp_store_tile_c(ws + B::DY, d1, g, t);
+      __syncwarp();
+      lp_dw<32, 4>(ws + B::AW_C0, ws + B::XC, ws + B::DY, lane);
+      db[3] += lp_colsum(ws + B::DY, lane);
+      lp_c_to_a_tf32(d1, a);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d1[mt][n][i] = 0.f;
+      lp_dx<4, 4>(smem + L::X_C0, d1, a, lane);  // d_xc (C-fragment order)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) genc[mt][n][i] += d1[mt][n][i];
+      // opacity hidden layer: dW_o0 += t^T d_ho', d_t = d_xc + d_ho' Wo0^T
+      __syncwarp();
+      lp_store_tile_c(ws + B::DY, d2, g, t);
+      __syncwarp();
+      lp_dw<32, 4>(ws + B::AW_O0, ws + B::TR, ws + B::DY, lane);
+      db[2] += lp_colsum(ws + B::DY, lane);
+      lp_c_to_a_tf32(d2, a);
+      lp_dx<4, 4>(smem + L::X_O0, d1, a, lane);  // d1 = d_t
+      lp_gate_c(d1, m_tr);
+      // trunk layer 1
+      __syncwarp();
+      lp_store_tile_c(ws + B::DY, d1, g, t);
+      __syncwarp();
+      lp_dw<32, 4>(ws + B::AW_T1, ws + B::H1, ws + B::DY, lane);
+      db[1] += lp_colsum(ws + B::DY, lane);
+      lp_c_to_a_tf32(d1, a);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d2[mt][n][i] = 0.f;
+      lp_dx<4, 4>(smem + L::X_T1, d2, a, lane);  // d_h1
+      lp_gate_c(d2, m_h1);
+      // trunk layer 0
+      __syncwarp();
+      lp_store_tile_c(ws + B::DY, d2, g, t);
+      __syncwarp();
+      lp_dw<C, 4>(ws + B::AW_T0, ws + B::X0, ws + B::DY, lane);
+      db[0] += lp_colsum(ws + B::DY, lane);
+      lp_c_to_a_tf32(d2, a);
+      float dx0[2][C / 8][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < C / 8; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dx0[mt][n][i] = 0.f;
+      lp_dx<C / 8, 4>(smem + L::X_T0, dx0, a, lane);
+      // scatter d_x0: row (mt,h) holds channels 16k+4t..+3 in (dx0[mt][2k][2h..], dx0[mt][2k+1][2h..])
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int mt = i >> 1, h = i & 1;
+        float d[C / 4];
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k) {
+          d[4 * k] = dx0[mt][2 * k][2 * h]; d[4 * k + 1] = dx0[mt][2 * k][2 * h + 1];
+          d[4 * k + 2] = dx0[mt][2 * k + 1][2 * h]; d[4 * k + 3] = dx0[mt][2 * k + 1][2 * h + 1];
+        }
+        if (r.active[i]) {
+          const SamplePos p = lp_sample_pos(r, i, step, M);
+          lp_splat_row<C>(G, io.g_grid, r.b[i], p.x, p.y, p.z, p.oob, t, d);
+        }
+      }
+    }
+    // ray-encoding gradient of this tile
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        if (r.active[2 * mt])
+          *reinterpret_cast<float2*>(io.g_enc + (long long)r.ray[2 * mt] * H + 8 * n + 2 * t) = make_float2(genc[mt][n][0], genc[mt][n][1]);
+        if (r.active[2 * mt + 1])
+          *reinterpret_cast<float2*>(io.g_enc + (long long)r.ray[2 * mt + 1] * H + 8 * n + 2 * t) = make_float2(genc[mt][n][2], genc[mt][n][3]);
+      }
+  }
+  // ---- flush the warp's parameter-gradient accumulators ----
+  __syncwarp();
+  {
+    const LpLayer &t0 = D.trunk.l[0], &t1 = D.trunk.l[1], &o0 = D.opacity.l[0], &o1 = D.opacity.l[1],
+                  &c0 = D.color.l[0], &c1 = D.color.l[1];
+    auto flush = [&](const float* acc, const LpLayer& Ly, int mfs) {
+      for (int mf = 0; mf < mfs; ++mf)
+        for (int nn = 0; nn < 4; ++nn) {
+          const float4 v = *reinterpret_cast<const float4*>(acc + ((mf * 4 + nn) * 32 + lane) * 4);
+          float* dst = io.g_params + Ly.w_off;
+          lp_red_add1(dst + (16 * mf + g) * Ly.N + 8 * nn + 2 * t, v.x);
+          lp_red_add1(dst + (16 * mf + g) * Ly.N + 8 * nn + 2 * t + 1, v.y);
+          lp_red_add1(dst + (16 * mf + g + 8) * Ly.N + 8 * nn + 2 * t, v.z);
+          lp_red_add1(dst + (16 * mf + g + 8) * Ly.N + 8 * nn + 2 * t + 1, v.w);
+        }
+    };
+    flush(ws + B::AW_T0, t0, C / 16);
+    flush(ws + B::AW_T1, t1, 2);
+    flush(ws + B::AW_O0, o0, 2);
+    flush(ws + B::AW_C0, c0, 2);
+    for (int mf = 0; mf < 2; ++mf) {  // last layer: columns (2t: colour t | 2t+1: opacity for t == 0)
+      const float4 vc = *reinterpret_cast<const float4*>(ws + B::AW_LC + (mf * 32 + lane) * 4);
+      const float4 vo = *reinterpret_cast<const float4*>(ws + B::AW_LO + (mf * 32 + lane) * 4);
+      if (t < D.n_feat) {
+        lp_red_add1(io.g_params + c1.w_off + (16 * mf + g) * c1.N + t, vc.x);
+        lp_red_add1(io.g_params + c1.w_off + (16 * mf + g + 8) * c1.N + t, vc.z);
+      }
+      if (t == 0) {
+        lp_red_add1(io.g_params + o1.w_off + (16 * mf + g), vo.y);
+        lp_red_add1(io.g_params + o1.w_off + (16 * mf + g + 8), vo.w);
+      }
+    }
+    lp_red_add1(io.g_params + t0.b_off + lane, db[0]);
+    lp_red_add1(io.g_params + t1.b_off + lane, db[1]);
+    lp_red_add1(io.g_params + o0.b_off + lane, db[2]);
+    lp_red_add1(io.g_params + c0.b_off + lane, db[3]);
+    if (lane < 8) {
+      if (lane & 1) { if (lane == 1) lp_red_add1(io.g_params + o1.b_off, db[4]); }
+      else if ((lane >> 1) < D.n_feat) lp_red_add1(io.g_params + c1.b_off + (lane >> 1), db[4]);
+    }
+  }
+}
+
 }  // namespace lpf
 
 // -------------------------------------------------------------------------------------------
@@ -427,7 +907,23 @@ static inline int lp_fast_render_forward(cudaStream_t st, const LpRenderArgs& a,
   return lp_fast_render_forward_t<32>(st, a, params, out_len, out_nlt, out_feat, feat_stride);
 }
 
-static inline bool lp_fast_render_backward_supported(const LpRenderArgs&) { return false; }
-static inline int lp_fast_render_backward(cudaStream_t, const LpRenderArgs&, const float*, const LpBwdIo&) {
-  return LP_ERR_UNSUPPORTED;
+static inline bool lp_fast_render_backward_supported(const LpRenderArgs& a) { return a.D.C == 16 || a.D.C == 32; }
+
+template <int C>
+static int lp_fast_render_backward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
+  // C=16: 4 warps x 38.4 KB + 49.7 KB weight image; C=32: 3 warps (shared-memory budget)
+  const int warps = (C == 16) ? 4 : 3;
+  const size_t bytes = 4ull * (lpf::Lay<C>::END + warps * lpf::BLay<C>::END);
+  if (LP_FAST_SET_SMEM(lpf::lp_render_bwd_fast_kernel<C>, bytes)) return LP_ERR_CUDA;
+  const int tiles = (a.R.n + 31) / 32;
+  int blocks = (tiles + warps - 1) / warps;
+  const int max_blocks = lp_fast_num_sms();  // persistent, one CTA per SM
+  if (blocks > max_blocks) blocks = max_blocks;
+  LP_LAUNCH(lpf::lp_render_bwd_fast_kernel<C>, dim3(blocks), dim3(warps * 32), bytes, st, a.R, a.M, a.D, a.G, params, io);
+  return LP_OK;
+}
+
+static inline int lp_fast_render_backward(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
+  if (a.D.C == 16) return lp_fast_render_backward_t<16>(st, a, params, io);
+  return lp_fast_render_backward_t<32>(st, a, params, io);
 }
