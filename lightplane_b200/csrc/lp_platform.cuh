@@ -78,3 +78,97 @@ LP_DEVICE void lp_mma_tf32(float (&d)[4], const float (&a)[4], const float (&b)[
         "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
 #endif
 }
+
+// ---------------------------------------------------------------------------------------------
+// Blackwell async tensor-core primitives used for the parameter-gradient GEMMs of the backward
+// kernel: accumulators live in TMEM (tcgen05), operands are bf16 tiles in shared memory laid out as
+// MN-major, non-swizzled UMMA operands: element (mn, k) at byte
+//     (mn/8)*SBO + (k/8)*LBO + (k%8)*16 + (mn%8)*2,   LBO = 128, SBO = 512
+// (validated in isolation by tools/tc_test.cu).  D[128 x N] (+)= A[128 x 16] * B[16 x N].
+// ---------------------------------------------------------------------------------------------
+#define LP_TC_LBO 128
+#define LP_TC_SBO 512
+
+LP_DEVICE unsigned lp_pack_bf16x2(float lo, float hi) {  // lo -> bits 0..15, hi -> bits 16..31
+#if defined(LP_HOSTSIM)
+  auto cv = [](float x) -> unsigned {
+    unsigned u = __float_as_uint(x);
+    if ((u & 0x7f800000u) == 0x7f800000u) return u >> 16;
+    u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even
+    return u >> 16;
+  };
+  return cv(lo) | (cv(hi) << 16);
+#else
+  unsigned r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+#endif
+}
+
+#if !defined(LP_HOSTSIM)
+LP_DEVICE unsigned lp_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+LP_DEVICE void lp_mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lp_smem_u32(bar)), "r"(count));
+}
+LP_DEVICE void lp_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+LP_DEVICE void lp_mbar_wait(unsigned long long* bar, int parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(lp_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+LP_DEVICE void lp_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+LP_DEVICE void lp_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+LP_DEVICE void lp_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// warp-collective (call from exactly one full warp)
+LP_DEVICE void lp_tmem_alloc512(unsigned* slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(lp_smem_u32(slot)) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+LP_DEVICE void lp_tmem_dealloc512(unsigned base) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+}
+LP_DEVICE unsigned long long lp_tc_desc(const void* smem_ptr) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((lp_smem_u32(smem_ptr) >> 4) & 0x3FFF);
+  d |= (unsigned long long)((LP_TC_LBO >> 4) & 0x3FFF) << 16;
+  d |= (unsigned long long)((LP_TC_SBO >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+// one elected thread: D(tmem column col, 128 lanes x n cols) (+)= A(128 x 16) * B(16 x n); bf16, MN-major
+LP_DEVICE void lp_tc_mma_bf16(unsigned tmem_base, int col, const void* a, const void* b, int n, int accumulate) {
+  const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(n >> 3) << 17) | (8u << 24);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_base + (unsigned)col),
+      "l"(lp_tc_desc(a)), "l"(lp_tc_desc(b)), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+LP_DEVICE void lp_tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(lp_smem_u32(bar)) : "memory");
+}
+// warp-collective: lane i receives 32 consecutive columns of TMEM lane 32*(warp%4)+i
+LP_DEVICE void lp_tmem_ld32(unsigned tmem_base, int lane_base, int col, float (&v)[32]) {
+  unsigned r[32];
+  const unsigned taddr = tmem_base + ((unsigned)lane_base << 16) + (unsigned)col;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+#endif  // !LP_HOSTSIM

@@ -214,63 +214,187 @@ LP_DEVICE void lp_relu_to_a(const float (&acc)[2][4][4], float (&a)[2][4][4]) {
     }
 }
 
-// Per-warp ray tile: geometry in registers for the lane's 4 rows (row i = 16*(i>>1) + 8*(i&1) + g).
-struct Rows {
-  float ox[4], oy[4], oz[4], dx[4], dy[4], dz[4], near[4], far[4];
-  int b[4], ray[4];
-  bool active[4];
+// -------------------------------------------------------------------------------------------
+// Ray geometry.  Sampling positions and taps are computed by the lane that OWNS the ray (lane r <->
+// ray rbase + r); the MLP works on quad-shared rows (row i of lane (g,t) = ray 16*(i>>1)+8*(i&1)+g).
+// Sampled features / their gradients cross between the two layouts through a small swizzled
+// shared-memory tile, so the tap arithmetic is done once per ray instead of once per lane of a quad.
+// -------------------------------------------------------------------------------------------
+struct Ray1 {
+  float ox, oy, oz, dx, dy, dz, near, far;
+  int b, ray;
+  bool active;
 };
+LP_DEVICE Ray1 lp_load_ray1(const LpRays& R, int ray, int batch) {
+  Ray1 r;
+  r.active = ray < R.n;
+  r.ray = ray;
+  const int q = r.active ? ray : R.n - 1;
+  r.ox = R.org[3 * q]; r.oy = R.org[3 * q + 1]; r.oz = R.org[3 * q + 2];
+  r.dx = R.dir[3 * q]; r.dy = R.dir[3 * q + 1]; r.dz = R.dir[3 * q + 2];
+  r.near = R.near[q]; r.far = R.far[q];
+  r.b = min(max(R.gidx[q], 0), batch - 1);
+  return r;
+}
 
-LP_DEVICE void lp_load_rows(const LpRays& R, int rbase, int g, int batch, Rows& r) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ray = rbase + 16 * (i >> 1) + 8 * (i & 1) + g;
-    r.active[i] = ray < R.n;
-    r.ray[i] = ray;
-    const int q = r.active[i] ? ray : R.n - 1;
-    r.ox[i] = R.org[3 * q]; r.oy[i] = R.org[3 * q + 1]; r.oz[i] = R.org[3 * q + 2];
-    r.dx[i] = R.dir[3 * q]; r.dy[i] = R.dir[3 * q + 1]; r.dz[i] = R.dir[3 * q + 2];
-    r.near[i] = R.near[q]; r.far[i] = R.far[q];
-    r.b[i] = min(max(R.gidx[q], 0), batch - 1);
+// warp-uniform depth schedule of one step: depth = a + b*c  with per-ray (a, b) chosen by `inf`
+struct Sched {
+  float cur, prev;  // regular: j/(S-1), (j-1)/(S-1);  background: 1/n_disp(k), 1/n_disp(k-1)
+  bool inf, first_inf, single;
+};
+LP_DEVICE Sched lp_sched(int step, const LpMarch& M) {
+  Sched s;
+  s.inf = step >= M.S;
+  s.single = M.S <= 1;
+  s.first_inf = step == M.S;
+  if (!s.inf) {
+    const float inv = s.single ? 0.f : 1.f / (float)(M.S - 1);
+    s.cur = (float)step * inv;
+    s.prev = (float)(step - 1) * inv;
+  } else {
+    const int k = step - M.S;
+    auto sc = [&](int kk) {  // 1 / ((1-f) + d_inf*f), f = (kk+1)/S_inf  (see lp_depth)
+      const float f = (float)(kk + 1) / (float)M.S_inf;
+      const float omf = (float)(M.S_inf - (kk + 1)) / (float)M.S_inf;
+      return 1.f / (omf + M.disparity_at_inf * f);
+    };
+    s.cur = sc(k);
+    s.prev = sc(k - 1);
+  }
+  return s;
+}
+LP_DEVICE void lp_depth_delta(const Sched& s, float near, float far, float& depth, float& delta) {
+  if (!s.inf) {
+    if (s.single) { depth = near; delta = 1.f; return; }
+    depth = (far - near) * s.cur + near;
+    delta = depth - ((far - near) * s.prev + near);
+  } else {
+    depth = far * s.cur;
+    delta = depth - (s.first_inf ? ((far - near) * 1.f + near) : far * s.prev);
   }
 }
 
-// Gather the lane's channel chunk(s) of one row's sample: xa[C/4] (chunk k = channels 16k+4t..+3).
-template <int C>
-LP_DEVICE void lp_gather_row(const LpGridSet& G, int b, float x, float y, float z, float oob, int t,
-                             float (&xa)[C / 4]) {
+// taps of one grid with 32-bit element offsets (the fast path requires < 2^31 grid elements)
+LP_DEVICE void lp_axis_i(float p, int size, int& i0, float& frac) {
+  float i = ((p + 1.f) * 0.5f) * (float)size - 0.5f;
+  if (size <= 1) i = 0.f;
+  const float f0 = floorf(i);
+  frac = i - f0;
+  i0 = (int)fminf(fmaxf(f0, -2.f), (float)size);  // clamp keeps the int conversion defined
+}
+LP_DEVICE void lp_corner_i(int i0, float frac, int size, float& w0, float& w1, int& c0, int& c1) {
+  w0 = ((unsigned)i0 < (unsigned)size) ? 1.f - frac : 0.f;
+  w1 = ((unsigned)(i0 + 1) < (unsigned)size) ? frac : 0.f;
+  c0 = min(max(i0, 0), size - 1);
+  c1 = min(max(i0 + 1, 0), size - 1);
+}
+LP_DEVICE int lp_taps_i32(const LpGrid& g, int C, int b, float x, float y, float z, int* off, float* w) {
+  if (g.kind == LP_VOXEL) {
+    int x0, y0, z0, cx[2], cy[2], cz[2];
+    float fx, fy, fz, wx[2], wy[2], wz[2];
+    lp_axis_i(x, g.W, x0, fx); lp_axis_i(y, g.H, y0, fy); lp_axis_i(z, g.D, z0, fz);
+    lp_corner_i(x0, fx, g.W, wx[0], wx[1], cx[0], cx[1]);
+    lp_corner_i(y0, fy, g.H, wy[0], wy[1], cy[0], cy[1]);
+    lp_corner_i(z0, fz, g.D, wz[0], wz[1], cz[0], cz[1]);
+    const int bbase = (int)g.base + b * g.D * g.H * g.W * C;
 #pragma unroll
-  for (int k = 0; k < C / 4; ++k) xa[k] = 0.f;
+    for (int c = 0; c < 8; ++c) {
+      w[c] = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
+      off[c] = bbase + ((cz[(c >> 2) & 1] * g.H + cy[(c >> 1) & 1]) * g.W + cx[c & 1]) * C;
+    }
+    return 8;
+  }
+  float u, v;
+  int U, V;
+  if (g.kind == LP_PLANE_XY) { u = x; v = y; U = g.W; V = g.H; }
+  else if (g.kind == LP_PLANE_XZ) { u = x; v = z; U = g.W; V = g.D; }
+  else { u = y; v = z; U = g.H; V = g.D; }
+  int u0, v0, cu[2], cv[2];
+  float fu, fv, wu[2], wv[2];
+  lp_axis_i(u, U, u0, fu); lp_axis_i(v, V, v0, fv);
+  lp_corner_i(u0, fu, U, wu[0], wu[1], cu[0], cu[1]);
+  lp_corner_i(v0, fv, V, wv[0], wv[1], cv[0], cv[1]);
+  const int bbase = (int)g.base + b * U * V * C;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    w[c] = wu[c & 1] * wv[c >> 1];
+    off[c] = bbase + (cv[c >> 1] * U + cu[c & 1]) * C;
+  }
+  return 4;
+}
+
+// float index of (ray row r, float4 chunk k) inside the per-warp [32][C] transfer tile; the XOR
+// makes both the row-wise float4 accesses of the ray-owner lanes and the chunk-wise accesses of
+// the quad lanes bank-conflict free
+template <int C>
+LP_DEVICE int lp_xs(int r, int k) {
+  if (C == 16) return r * 16 + ((k ^ ((r >> 1) & 3)) << 2);
+  return r * 32 + ((k ^ (((r & 1) << 2) | ((r >> 1) & 3))) << 2);
+}
+
+// The ray-owner lane samples all C channels of its sample point and drops them into the tile.
+template <int C>
+LP_DEVICE void lp_gather_lane(const LpGridSet& G, int b, float x, float y, float z, float oob, float* xs, int lane) {
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
   for (int gi = 0; gi < G.n; ++gi) {
-    long long off[8];
+    int off[8];
     float w[8];
-    const int nt = lp_taps(G.g[gi], C, b, x, y, z, off, w);
+    const int nt = lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
 #pragma unroll
     for (int tp = 0; tp < 8; ++tp) {
       if (tp < nt && w[tp] != 0.f) {
 #pragma unroll
-        for (int k = 0; k < C / 16; ++k) {
-          const float4 v = lp_ldg4(G.data + off[tp] + 16 * k + 4 * t);
-          xa[4 * k + 0] = fmaf(w[tp], v.x, xa[4 * k + 0]); xa[4 * k + 1] = fmaf(w[tp], v.y, xa[4 * k + 1]);
-          xa[4 * k + 2] = fmaf(w[tp], v.z, xa[4 * k + 2]); xa[4 * k + 3] = fmaf(w[tp], v.w, xa[4 * k + 3]);
+        for (int k = 0; k < C / 4; ++k) {
+          const float4 v = lp_ldg4(G.data + off[tp] + 4 * k);
+          acc[4 * k] = fmaf(w[tp], v.x, acc[4 * k]); acc[4 * k + 1] = fmaf(w[tp], v.y, acc[4 * k + 1]);
+          acc[4 * k + 2] = fmaf(w[tp], v.z, acc[4 * k + 2]); acc[4 * k + 3] = fmaf(w[tp], v.w, acc[4 * k + 3]);
         }
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < C / 4; ++k) xa[k] *= oob;
+  for (int k = 0; k < C / 4; ++k)
+    *reinterpret_cast<float4*>(xs + lp_xs<C>(lane, k)) =
+        make_float4(acc[4 * k] * oob, acc[4 * k + 1] * oob, acc[4 * k + 2] * oob, acc[4 * k + 3] * oob);
 }
-
-// Sample position, step length etc. of one row at `step`.
-struct SamplePos { float x, y, z, depth, delta, oob; };
-LP_DEVICE SamplePos lp_sample_pos(const Rows& r, int i, int step, const LpMarch& M) {
-  SamplePos p;
-  p.depth = lp_depth(step, r.near[i], r.far[i], M.S, M.S_inf, M.disparity_at_inf);
-  p.delta = p.depth - lp_depth(step - 1, r.near[i], r.far[i], M.S, M.S_inf, M.disparity_at_inf);
-  p.x = r.ox[i] + p.depth * r.dx[i]; p.y = r.oy[i] + p.depth * r.dy[i]; p.z = r.oz[i] + p.depth * r.dz[i];
-  if (M.contract) lp_contract(p.x, p.y, p.z);
-  p.oob = M.mask_oob ? lp_in_bounds(p.x, p.y, p.z) : 1.f;
-  return p;
+// quad lane (g,t): channel chunk(s) t (and 4+t) of its four rows
+template <int C>
+LP_DEVICE void lp_read_rows(const float* xs, int g, int t, float (&xa)[4][C / 4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < C / 16; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(xs + lp_xs<C>(8 * i + g, 4 * k + t));
+      xa[i][4 * k] = v.x; xa[i][4 * k + 1] = v.y; xa[i][4 * k + 2] = v.z; xa[i][4 * k + 3] = v.w;
+    }
+}
+// adjoint: the ray-owner lane scatters its row of the tile into the grid gradient
+template <int C>
+LP_DEVICE void lp_splat_lane(const LpGridSet& G, float* grad, int b, float x, float y, float z, float oob,
+                             const float* xs, int lane) {
+  if (oob == 0.f) return;
+  float d[C];
+#pragma unroll
+  for (int k = 0; k < C / 4; ++k) {
+    const float4 v = *reinterpret_cast<const float4*>(xs + lp_xs<C>(lane, k));
+    d[4 * k] = v.x * oob; d[4 * k + 1] = v.y * oob; d[4 * k + 2] = v.z * oob; d[4 * k + 3] = v.w * oob;
+  }
+  for (int gi = 0; gi < G.n; ++gi) {
+    int off[8];
+    float w[8];
+    const int nt = lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
+#pragma unroll
+    for (int tp = 0; tp < 8; ++tp) {
+      if (tp < nt && w[tp] != 0.f) {
+#pragma unroll
+        for (int k = 0; k < C / 4; ++k)
+          lp_red_add4(grad + off[tp] + 4 * k, w[tp] * d[4 * k], w[tp] * d[4 * k + 1], w[tp] * d[4 * k + 2],
+                      w[tp] * d[4 * k + 3]);
+      }
+    }
+  }
 }
 
 // x0 rows -> A-fragments of the first trunk layer
@@ -292,7 +416,7 @@ LP_DEVICE void lp_x0_to_a(const float (&xa)[4][C / 4], float (&a)[2][C / 8][4]) 
 // forward
 // ===========================================================================================
 template <int C>
-__global__ void __launch_bounds__(256) lp_render_fwd_fast_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
+__global__ void __launch_bounds__(256, 2) lp_render_fwd_fast_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
                                                                 const float* __restrict__ params,
                                                                 float* __restrict__ out_len,
                                                                 float* __restrict__ out_nlt,
@@ -303,15 +427,21 @@ __global__ void __launch_bounds__(256) lp_render_fwd_fast_kernel(LpRays R, LpMar
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  float* enc_s = smem + L::FWD_END + warp * (32 * 40);  // per-warp [32 rays][40] encoding tile
+  float* enc_s = smem + L::FWD_END + warp * (32 * 40 + 32 * C);  // per-warp [32 rays][40] encoding tile
+  float* xs = enc_s + 32 * 40;                                    // per-warp [32][C] transfer tile
   const float* bias = smem + L::BIAS;
   const int num_tiles = (R.n + 31) / 32;
   const int tot = M.S + M.S_inf;
 
   for (int tile = blockIdx.x * nwarps + warp; tile < num_tiles; tile += gridDim.x * nwarps) {
     const int rbase = tile * 32;
-    Rows r;
-    lp_load_rows(R, rbase, g, G.g[0].B, r);
+    const Ray1 me = lp_load_ray1(R, rbase + lane, G.g[0].B);
+    float rnear[4], rfar[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      rnear[i] = __shfl_sync(LP_FULL_MASK, me.near, 8 * i + g);
+      rfar[i] = __shfl_sync(LP_FULL_MASK, me.far, 8 * i + g);
+    }
     __syncwarp();
     for (int e = lane; e < 32 * 8; e += 32) {  // 32 rays x 8 float4
       const int row = e >> 3, c4 = e & 7;
@@ -322,13 +452,21 @@ __global__ void __launch_bounds__(256) lp_render_fwd_fast_kernel(LpRays R, LpMar
     float nlt[4] = {0.f, 0.f, 0.f, 0.f}, T[4] = {1.f, 1.f, 1.f, 1.f}, accum[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (int step = 0; step < tot; ++step) {
+      const Sched sc = lp_sched(step, M);
       float xa[4][C / 4], depth[4], delta[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const SamplePos p = lp_sample_pos(r, i, step, M);
-        depth[i] = p.depth; delta[i] = p.delta;
-        lp_gather_row<C>(G, r.b[i], p.x, p.y, p.z, p.oob, t, xa[i]);
+      {
+        float dep, del;
+        lp_depth_delta(sc, me.near, me.far, dep, del);
+        float x = me.ox + dep * me.dx, y = me.oy + dep * me.dy, z = me.oz + dep * me.dz;
+        if (M.contract) lp_contract(x, y, z);
+        const float oob = M.mask_oob ? lp_in_bounds(x, y, z) : 1.f;
+        __syncwarp();  // previous step's readers are done with the tile
+        lp_gather_lane<C>(G, me.b, x, y, z, oob, xs, lane);
+        __syncwarp();
+        lp_read_rows<C>(xs, g, t, xa);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) lp_depth_delta(sc, rnear[i], rfar[i], depth[i], delta[i]);
       float acc[2][4][4], a[2][4][4];
       {
         float a0[2][C / 8][4];
@@ -367,7 +505,7 @@ __global__ void __launch_bounds__(256) lp_render_fwd_fast_kernel(LpRays R, LpMar
       for (int i = 0; i < 4; ++i) {
         const int mt = i >> 1, h = i & 1;
         float raw = last[mt][2 * h + 1];
-        if (M.noise) raw += M.sigma * lp_sample_noise(M, r.ray[i], step);
+        if (M.noise) raw += M.sigma * lp_sample_noise(M, rbase + 8 * i + g, step);
         nlt[i] += delta[i] * M.gain * lp_softplus(raw);
         const float Tn = expf(-nlt[i]);
         const float w = T[i] - Tn;
@@ -377,9 +515,10 @@ __global__ void __launch_bounds__(256) lp_render_fwd_fast_kernel(LpRays R, LpMar
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (r.active[i]) {
-        if (t < D.n_feat) out_feat[(long long)r.ray[i] * feat_stride + t] = accum[i];
-        if (t == 3) { out_len[r.ray[i]] = accum[i]; out_nlt[r.ray[i]] = nlt[i]; }
+      const int ray = rbase + 8 * i + g;
+      if (ray < R.n) {
+        if (t < D.n_feat) out_feat[(long long)ray * feat_stride + t] = accum[i];
+        if (t == 3) { out_len[ray] = accum[i]; out_nlt[ray] = nlt[i]; }
       }
     }
   }
@@ -389,36 +528,23 @@ __global__ void __launch_bounds__(256) lp_render_fwd_fast_kernel(LpRays R, LpMar
 // ===========================================================================================
 // backward
 // ===========================================================================================
-// Shared-memory tiles of one warp (32 samples), all [sample][feature] with an XOR swizzle of the
-// feature index by 8*(sample&3) so that both the C-fragment stores (float2 per lane) and the
-// transposed fragment loads of the dW products are bank-conflict free without padding.
-LP_DEVICE int lp_sw32(int s, int f) { return s * 32 + (f ^ ((s & 3) << 3)); }
-LP_DEVICE int lp_sw16(int s, int f) { return s * 16 + (f ^ (((s >> 1) & 1) << 3)); }
+// The register-resident chain (3xTF32 recompute, TF32 dX) stays on mma.sync; the parameter-gradient
+// GEMMs  dW_l += X_l^T dY_l  -- a reduction over EVERY sample the CTA ever touches -- run on the
+// 5th-generation tensor cores: each warp drops bf16 copies of its activations X_l and gradients dY_l
+// (32 samples) into shared memory as MN-major UMMA operands and issues tcgen05.mma instructions that
+// accumulate into ONE set of fp32 accumulators per CTA held in TMEM for the whole kernel (144 KB of
+// accumulator state per CTA would otherwise live in registers / shared memory and cap the kernel at
+// 4 warps per SM).  bf16 rounding of X / dY is unbiased and independent per sample, so it averages
+// out over the millions of samples reduced into each dW entry.
+//
+// Operand stacks of one warp (rows = features, 32 samples each, see lp_platform.cuh for the layout):
+//   A1 = [h1 (32) | trunk (32) | trunk+enc (32) | x0 (C, zero padded to 32)]        128 rows
+//   A2 = [colour hidden (32) | opacity hidden (32) | ones (1) | ...]                128 rows (65 used)
+//   B_j = dY of trunk layer 1, opacity hidden, colour hidden, trunk layer 0 (32 wide), B_last (16 wide)
+// TMEM columns:  [0,128): A1 x B_j -> dW of the four 32-wide layers on the block diagonal;
+//                [128,256): A2 x B_j -> row 64 (ones) = bias gradients;  [256,272): A2 x B_last.
 
-// store an activation given in A-fragment order (see lp_relu_to_a) as TF32 into a 32-wide tile
-LP_DEVICE void lp_store_tile_a(float* tile, const float (&a)[2][4][4], int g, int t) {
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      *reinterpret_cast<float2*>(tile + lp_sw32(16 * mt + g, 8 * n + 2 * t)) =
-          make_float2(lp_tf32_rna(a[mt][n][0]), lp_tf32_rna(a[mt][n][2]));
-      *reinterpret_cast<float2*>(tile + lp_sw32(16 * mt + 8 + g, 8 * n + 2 * t)) =
-          make_float2(lp_tf32_rna(a[mt][n][1]), lp_tf32_rna(a[mt][n][3]));
-    }
-}
-// same for a gradient held in C-fragment order
-LP_DEVICE void lp_store_tile_c(float* tile, const float (&c)[2][4][4], int g, int t) {
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      *reinterpret_cast<float2*>(tile + lp_sw32(16 * mt + g, 8 * n + 2 * t)) =
-          make_float2(lp_tf32_rna(c[mt][n][0]), lp_tf32_rna(c[mt][n][1]));
-      *reinterpret_cast<float2*>(tile + lp_sw32(16 * mt + 8 + g, 8 * n + 2 * t)) =
-          make_float2(lp_tf32_rna(c[mt][n][2]), lp_tf32_rna(c[mt][n][3]));
-    }
-}
+LP_DEVICE int lp_sw32(int s, int f) { return s * 32 + (f ^ ((s & 3) << 3)); }
 
 // ReLU mask of an activation in A-fragment order: bit (mt*16 + n*4 + i) set iff a[mt][n][i] > 0
 LP_DEVICE unsigned lp_mask_a(const float (&a)[2][4][4]) {
@@ -471,135 +597,128 @@ LP_DEVICE void lp_dx(const float* Xf, float (&acc)[2][NN][4], const float (&a)[2
     }
 }
 
-// dW tile update over the warp's 32 samples:  acc[mf][nn] += X^T(features 16mf.., samples) * dY
-// X tile [32][KF] (swizzled), dY tile [32][NO*8]; accumulators live in smem in fragment order.
-template <int KF, int NO>
-LP_DEVICE void lp_dw(float* accum, const float* X, const float* dY, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  constexpr int MF = KF / 16;
-  float c[MF][NO][4];
+// bf16 operand tiles (byte offsets): feature f (0..31 of the block starting at chunk `chunk0`),
+// sample s = 16mt + 8h + g  ->  (chunk0 + f/8)*512 + (2mt+h)*128 + g*16 + (f%8)*2
+LP_DEVICE void lp_tile_put_a(unsigned char* stack, int chunk0, const float (&a)[2][4][4], int g, int t) {
 #pragma unroll
-  for (int mf = 0; mf < MF; ++mf)
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nn = 0; nn < NO; ++nn) {
-      const float4 v = *reinterpret_cast<const float4*>(accum + ((mf * NO + nn) * 32 + lane) * 4);
-      c[mf][nn][0] = v.x; c[mf][nn][1] = v.y; c[mf][nn][2] = v.z; c[mf][nn][3] = v.w;
+    for (int n = 0; n < 4; ++n) {  // A-fragment order: (a0,a2) = row g, (a1,a3) = row g+8
+      unsigned char* p = stack + (chunk0 + n) * LP_TC_SBO + (2 * mt) * LP_TC_LBO + g * 16 + 4 * t;
+      *reinterpret_cast<unsigned*>(p) = lp_pack_bf16x2(a[mt][n][0], a[mt][n][2]);
+      *reinterpret_cast<unsigned*>(p + LP_TC_LBO) = lp_pack_bf16x2(a[mt][n][1], a[mt][n][3]);
     }
+}
+LP_DEVICE void lp_tile_put_c(unsigned char* tile, const float (&c)[2][4][4], int g, int t) {
 #pragma unroll
-  for (int js = 0; js < 4; ++js) {
-    float a[MF][4];
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int mf = 0; mf < MF; ++mf) {
-      if (KF == 16) {
-        a[mf][0] = X[lp_sw16(8 * js + t, g)];     a[mf][1] = X[lp_sw16(8 * js + t, g + 8)];
-        a[mf][2] = X[lp_sw16(8 * js + t + 4, g)]; a[mf][3] = X[lp_sw16(8 * js + t + 4, g + 8)];
-      } else {
-        a[mf][0] = X[lp_sw32(8 * js + t, 16 * mf + g)];     a[mf][1] = X[lp_sw32(8 * js + t, 16 * mf + g + 8)];
-        a[mf][2] = X[lp_sw32(8 * js + t + 4, 16 * mf + g)]; a[mf][3] = X[lp_sw32(8 * js + t + 4, 16 * mf + g + 8)];
-      }
+    for (int n = 0; n < 4; ++n) {  // C-fragment order: (c0,c1) = row g, (c2,c3) = row g+8
+      unsigned char* p = tile + n * LP_TC_SBO + (2 * mt) * LP_TC_LBO + g * 16 + 4 * t;
+      *reinterpret_cast<unsigned*>(p) = lp_pack_bf16x2(c[mt][n][0], c[mt][n][1]);
+      *reinterpret_cast<unsigned*>(p + LP_TC_LBO) = lp_pack_bf16x2(c[mt][n][2], c[mt][n][3]);
     }
-#pragma unroll
-    for (int nn = 0; nn < NO; ++nn) {
-      const float b[2] = {dY[lp_sw32(8 * js + t, 8 * nn + g)], dY[lp_sw32(8 * js + t + 4, 8 * nn + g)]};
-#pragma unroll
-      for (int mf = 0; mf < MF; ++mf) lp_mma_tf32(c[mf][nn], a[mf], b);
-    }
-  }
-#pragma unroll
-  for (int mf = 0; mf < MF; ++mf)
-#pragma unroll
-    for (int nn = 0; nn < NO; ++nn)
-      *reinterpret_cast<float4*>(accum + ((mf * NO + nn) * 32 + lane) * 4) =
-          make_float4(c[mf][nn][0], c[mf][nn][1], c[mf][nn][2], c[mf][nn][3]);
 }
 
-// bias gradient: lane n accumulates the column sum of the dY tile
-LP_DEVICE float lp_colsum(const float* dY, int lane) {
-  float s = 0.f;
-#pragma unroll 8
-  for (int r = 0; r < 32; ++r) s += dY[lp_sw32(r, lane)];
-  return s;
-}
-
-// scatter one row's channel chunk(s) of d_x0 into the grid gradient
-template <int C>
-LP_DEVICE void lp_splat_row(const LpGridSet& G, float* grad, int b, float x, float y, float z, float oob, int t,
-                            const float (&d)[C / 4]) {
-  if (oob == 0.f) return;
-  for (int gi = 0; gi < G.n; ++gi) {
-    long long off[8];
-    float w[8];
-    const int nt = lp_taps(G.g[gi], C, b, x, y, z, off, w);
-#pragma unroll
-    for (int tp = 0; tp < 8; ++tp) {
-      if (tp < nt && w[tp] != 0.f) {
-        const float ww = w[tp] * oob;
-#pragma unroll
-        for (int k = 0; k < C / 16; ++k)
-          lp_red_add4(grad + off[tp] + 16 * k + 4 * t, ww * d[4 * k], ww * d[4 * k + 1], ww * d[4 * k + 2],
-                      ww * d[4 * k + 3]);
-      }
-    }
-  }
-}
-
-// per-warp shared-memory map of the backward kernel (floats)
-template <int C>
-struct BLay {
-  static constexpr int X0 = 0;                 // [32][C]
-  static constexpr int H1 = X0 + 32 * C;       // [32][32] each
-  static constexpr int TR = H1 + 1024;
-  static constexpr int XC = TR + 1024;
-  static constexpr int HO = XC + 1024;
-  static constexpr int HC = HO + 1024;
-  static constexpr int DY = HC + 1024;         // gradient tile (B operand of dW, bias sums)
-  static constexpr int AW_T0 = DY + 1024;      // dW accumulators, fragment order [mf][nn][32][4]
-  static constexpr int AW_T1 = AW_T0 + C * 32;
-  static constexpr int AW_O0 = AW_T1 + 1024;
-  static constexpr int AW_C0 = AW_O0 + 1024;
-  static constexpr int AW_LC = AW_C0 + 1024;   // hc^T * dY_last [2][1][32][4]
-  static constexpr int AW_LO = AW_LC + 256;    // ho^T * dY_last
-  static constexpr int RAYS = AW_LO + 256;     // per ray: total, g_nlt, g_len  [3][32]
-  static constexpr int END = RAYS + 96;
+// per-warp shared memory of the backward kernel (bytes)
+struct BW {
+  static constexpr int A1 = 0;                 // 16 chunks x 512 B
+  static constexpr int A2 = A1 + 8192;         // 9 chunks used; the MMA's 16-chunk window runs on into
+  static constexpr int DY = A2 + 9 * 512;      //   the gradient tiles behind it (finite data, rows unused)
+  static constexpr int DYL = DY + 4 * 2048;    // last-layer gradient tile [32 samples][16]
+  static constexpr int RAYS = DYL + 1024;      // fp32 [3][32]: total, g_nlt, g_len per ray
+  static constexpr int XS = RAYS + 384;        // fp32 [32][C] transfer tile (ray-owner <-> quad rows)
 };
+template <int C>
+struct BWEnd { static constexpr int value = BW::XS + 32 * C * 4; };
+// TMEM columns
+constexpr int TM_W = 0, TM_B = 128, TM_L = 256;
+
+// lane 0 of a warp: reduce this warp's 32 samples into the CTA's TMEM accumulators
+LP_DEVICE void lp_issue_dw(unsigned tmem, const unsigned char* wsb, int accumulate) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      lp_tc_mma_bf16(tmem, TM_W + 32 * j, wsb + BW::A1 + ks * 2 * LP_TC_LBO, wsb + BW::DY + j * 2048 + ks * 2 * LP_TC_LBO, 32,
+                     accumulate | ks);
+      lp_tc_mma_bf16(tmem, TM_B + 32 * j, wsb + BW::A2 + ks * 2 * LP_TC_LBO, wsb + BW::DY + j * 2048 + ks * 2 * LP_TC_LBO, 32,
+                     accumulate | ks);
+    }
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+    lp_tc_mma_bf16(tmem, TM_L, wsb + BW::A2 + ks * 2 * LP_TC_LBO, wsb + BW::DYL + ks * 2 * LP_TC_LBO, 16, accumulate | ks);
+}
 
 template <int C>
-__global__ void __launch_bounds__(128) lp_render_bwd_fast_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
+__global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
                                                                 const float* __restrict__ params, LpBwdIo io) {
   using L = Lay<C>;
-  using B = BLay<C>;
   LP_DYN_SMEM(float, smem);
-  lp_build_weights<C, true>(smem, params, D);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  float* ws = smem + L::END + warp * B::END;
-  for (int e = lane; e < B::RAYS - B::AW_T0; e += 32) ws[B::AW_T0 + e] = 0.f;
-  float db[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // bias gradients: lane n owns column n (t0,t1,o0,c0,last)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + L::END);  // [nwarps] + 1
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 9);
+  unsigned char* wsb = reinterpret_cast<unsigned char*>(smem + L::END + 32) + warp * BWEnd<C>::value;
+  float* wsf = reinterpret_cast<float*>(wsb + BW::RAYS);
+  float* xs = reinterpret_cast<float*>(wsb + BW::XS);
+
+  lp_build_weights<C, true>(smem, params, D);
+  for (int e = lane; e < BW::RAYS / 4; e += 32) reinterpret_cast<unsigned*>(wsb)[e] = 0u;  // zero all operand tiles
+  __syncwarp();
+  if (lane < 32) {  // the row of ones of A2 (stack row 64 = chunk 8, element 0), bf16 1.0 = 0x3F80
+    const int s = lane;
+    *reinterpret_cast<unsigned short*>(wsb + BW::A2 + 8 * LP_TC_SBO + (s >> 3) * LP_TC_LBO + (s & 7) * 16) = 0x3F80;
+  }
+  if (threadIdx.x == 0) {
+    for (int w = 0; w <= nwarps; ++w) lp_mbar_init(bars + w, 1);
+    lp_mbar_init_fence();
+  }
+  if (warp == 0) lp_tmem_alloc512(tmem_slot);
+  lp_fence_async_smem();
+  lp_tc_fence_before();
   __syncthreads();
+  lp_tc_fence_after();
+  const unsigned tmem = *tmem_slot;
+  if (threadIdx.x == 0) {  // zero the accumulators: D = 0 * 0 with accumulate off (dY tiles are zero)
+    lp_issue_dw(tmem, wsb, 0);
+    lp_tc_commit(bars + nwarps);
+  }
+  lp_mbar_wait(bars + nwarps, 0);
+  lp_tc_fence_after();
+  __syncthreads();
+
   const float* bias = smem + L::BIAS;
   const int num_tiles = (R.n + 31) / 32;
   const int tot = M.S + M.S_inf;
+  int iter = 0;  // number of operand hand-offs this warp has made
 
   for (int tile = blockIdx.x * nwarps + warp; tile < num_tiles; tile += gridDim.x * nwarps) {
     const int rbase = tile * 32;
-    Rows r;
-    lp_load_rows(R, rbase, g, G.g[0].B, r);
-    __syncwarp();
-    {  // per-ray constants computed by the lane that owns the ray
-      const int ray = rbase + lane;
-      const bool act = ray < R.n;
-      const int q = act ? ray : R.n - 1;
-      float gl = act ? io.g_len[q] : 0.f, gn = act ? io.g_nlt[q] : 0.f;
+    const Ray1 me = lp_load_ray1(R, rbase + lane, G.g[0].B);
+    float rnear[4], rfar[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      rnear[i] = __shfl_sync(LP_FULL_MASK, me.near, 8 * i + g);
+      rfar[i] = __shfl_sync(LP_FULL_MASK, me.far, 8 * i + g);
+    }
+    {  // per-ray constants computed by the lane that owns the ray (wsf is private to the warp and not
+       // an MMA operand, so no hand-off wait is needed here)
+      const int q = me.active ? me.ray : R.n - 1;
+      const float gl = me.active ? io.g_len[q] : 0.f, gn = me.active ? io.g_nlt[q] : 0.f;
       float tot_ = gl * io.len[q];
       for (int c = 0; c < D.n_feat; ++c)
-        tot_ = fmaf(act ? io.g_feat[(long long)q * io.g_feat_stride + c] : 0.f, io.feat[(long long)q * io.feat_stride + c], tot_);
-      ws[B::RAYS + lane] = tot_; ws[B::RAYS + 32 + lane] = gn; ws[B::RAYS + 64 + lane] = gl;
+        tot_ = fmaf(me.active ? io.g_feat[(long long)q * io.g_feat_stride + c] : 0.f, io.feat[(long long)q * io.feat_stride + c], tot_);
+      __syncwarp();
+      wsf[lane] = tot_; wsf[32 + lane] = gn; wsf[64 + lane] = gl;
     }
     __syncwarp();
     float nlt[4] = {0.f, 0.f, 0.f, 0.f}, T[4] = {1.f, 1.f, 1.f, 1.f}, prefix[4] = {0.f, 0.f, 0.f, 0.f}, gF[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      gF[i] = (r.active[i] && t < D.n_feat) ? io.g_feat[(long long)r.ray[i] * io.g_feat_stride + t] : 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const int ray = rbase + 8 * i + g;
+      gF[i] = (ray < R.n && t < D.n_feat) ? io.g_feat[(long long)ray * io.g_feat_stride + t] : 0.f;
+    }
     float genc[2][4][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -609,24 +728,35 @@ __global__ void __launch_bounds__(128) lp_render_bwd_fast_kernel(LpRays R, LpMar
         for (int i = 0; i < 4; ++i) genc[mt][n][i] = 0.f;
 
     for (int step = 0; step < tot; ++step) {
+      // operand tiles of the previous hand-off must have been consumed by the tensor core
+      if (iter > 0) lp_mbar_wait(bars + warp, (iter - 1) & 1);
       // ------------------------------ forward recompute ------------------------------
+      const Sched sc = lp_sched(step, M);
       float depth[4], delta[4];
       unsigned m_h1, m_tr, m_ho, m_hc;
       float last[2][4];
+      float sx, sy, sz, soob;  // the owned ray's sample position (reused by the scatter)
       {
         float xa[4][C / 4];
+        {
+          float dep, del;
+          lp_depth_delta(sc, me.near, me.far, dep, del);
+          sx = me.ox + dep * me.dx; sy = me.oy + dep * me.dy; sz = me.oz + dep * me.dz;
+          if (M.contract) lp_contract(sx, sy, sz);
+          soob = M.mask_oob ? lp_in_bounds(sx, sy, sz) : 1.f;
+          __syncwarp();
+          lp_gather_lane<C>(G, me.b, sx, sy, sz, soob, xs, lane);
+          __syncwarp();
+          lp_read_rows<C>(xs, g, t, xa);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const SamplePos p = lp_sample_pos(r, i, step, M);
-          depth[i] = p.depth; delta[i] = p.delta;
-          lp_gather_row<C>(G, r.b[i], p.x, p.y, p.z, p.oob, t, xa[i]);
-          const int s = 16 * (i >> 1) + 8 * (i & 1) + g;
+          lp_depth_delta(sc, rnear[i], rfar[i], depth[i], delta[i]);
 #pragma unroll
-          for (int k = 0; k < C / 16; ++k) {
-            const float4 v = make_float4(lp_tf32_rna(xa[i][4 * k]), lp_tf32_rna(xa[i][4 * k + 1]),
-                                         lp_tf32_rna(xa[i][4 * k + 2]), lp_tf32_rna(xa[i][4 * k + 3]));
-            if (C == 16) *reinterpret_cast<float4*>(ws + B::X0 + lp_sw16(s, 4 * t)) = v;
-            else *reinterpret_cast<float4*>(ws + B::X0 + lp_sw32(s, 16 * k + 4 * t)) = v;
+          for (int k = 0; k < C / 16; ++k) {  // x0 block of A1: stack rows 96 + 16k + 4t .. +3, sample-group i
+            unsigned char* p8 = wsb + BW::A1 + (12 + 2 * k + (t >> 1)) * LP_TC_SBO + i * LP_TC_LBO + g * 16 + 8 * (t & 1);
+            *reinterpret_cast<uint2*>(p8) = make_uint2(lp_pack_bf16x2(xa[i][4 * k], xa[i][4 * k + 1]),
+                                                       lp_pack_bf16x2(xa[i][4 * k + 2], xa[i][4 * k + 3]));
           }
         }
         float acc[2][4][4], a[2][4][4], tr[2][4][4];
@@ -638,35 +768,35 @@ __global__ void __launch_bounds__(128) lp_render_bwd_fast_kernel(LpRays R, LpMar
         }
         lp_relu_to_a(acc, a);
         m_h1 = lp_mask_a(a);
-        lp_store_tile_a(ws + B::H1, a, g, t);
+        lp_tile_put_a(wsb + BW::A1, 0, a, g, t);
         lp_init_bias(acc, bias + 32, t);
         lp_layer3x<4>(smem + L::F_T1, acc, a, lane);
         lp_relu_to_a(acc, tr);
         m_tr = lp_mask_a(tr);
-        lp_store_tile_a(ws + B::TR, tr, g, t);
+        lp_tile_put_a(wsb + BW::A1, 4, tr, g, t);
         lp_init_bias(acc, bias + 64, t);
         lp_layer3x<4>(smem + L::F_O0, acc, tr, lane);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) { last[mt][0] = last[mt][2] = bias[128 + 2 * t]; last[mt][1] = last[mt][3] = bias[128 + 2 * t + 1]; }
         lp_relu_to_a(acc, a);
         m_ho = lp_mask_a(a);
-        lp_store_tile_a(ws + B::HO, a, g, t);
+        lp_tile_put_a(wsb + BW::A2, 4, a, g, t);
         lp_layer3x_n1(smem + L::F_LO, last, a, lane);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int n = 0; n < 4; ++n) {
-            const int q0 = r.active[2 * mt] ? r.ray[2 * mt] : R.n - 1, q1 = r.active[2 * mt + 1] ? r.ray[2 * mt + 1] : R.n - 1;
+            const int q0 = min(rbase + 16 * mt + g, R.n - 1), q1 = min(rbase + 16 * mt + 8 + g, R.n - 1);
             const float2 e0 = __ldg(reinterpret_cast<const float2*>(R.enc + (long long)q0 * H + 8 * n + 2 * t));
             const float2 e1 = __ldg(reinterpret_cast<const float2*>(R.enc + (long long)q1 * H + 8 * n + 2 * t));
             tr[mt][n][0] += e0.x; tr[mt][n][2] += e0.y; tr[mt][n][1] += e1.x; tr[mt][n][3] += e1.y;
           }
-        lp_store_tile_a(ws + B::XC, tr, g, t);
+        lp_tile_put_a(wsb + BW::A1, 8, tr, g, t);
         lp_init_bias(acc, bias + 96, t);
         lp_layer3x<4>(smem + L::F_C0, acc, tr, lane);
         lp_relu_to_a(acc, a);
         m_hc = lp_mask_a(a);
-        lp_store_tile_a(ws + B::HC, a, g, t);
+        lp_tile_put_a(wsb + BW::A2, 0, a, g, t);
         lp_layer3x_n1(smem + L::F_LC, last, a, lane);
       }
       // ------------------------------ compositing gradient ------------------------------
@@ -675,7 +805,7 @@ __global__ void __launch_bounds__(128) lp_render_bwd_fast_kernel(LpRays R, LpMar
       for (int i = 0; i < 4; ++i) {
         const int mt = i >> 1, h = i & 1, s = 16 * mt + 8 * h + g;
         float raw = last[mt][2 * h + 1];
-        if (M.noise) raw += M.sigma * lp_sample_noise(M, r.ray[i], step);
+        if (M.noise) raw += M.sigma * lp_sample_noise(M, rbase + s, step);
         nlt[i] += delta[i] * M.gain * lp_softplus(raw);
         const float Tn = expf(-nlt[i]);
         const float w = T[i] - Tn;
@@ -684,31 +814,21 @@ __global__ void __launch_bounds__(128) lp_render_bwd_fast_kernel(LpRays R, LpMar
         float pc = (t < D.n_feat) ? sg * gF[i] : 0.f;  // this lane's colour channel
         pc += __shfl_xor_sync(LP_FULL_MASK, pc, 1);
         pc += __shfl_xor_sync(LP_FULL_MASK, pc, 2);
-        const float p = fmaf(depth[i], ws[B::RAYS + 64 + s], pc);
+        const float p = fmaf(depth[i], wsf[64 + s], pc);
         prefix[i] = fmaf(w, p, prefix[i]);
-        const float suffix = (step == tot - 1) ? 0.f : ws[B::RAYS + s] - prefix[i];
-        const float g_dop = Tn * p - suffix + ws[B::RAYS + 32 + s];
+        const float suffix = (step == tot - 1) ? 0.f : wsf[s] - prefix[i];
+        const float g_dop = Tn * p - suffix + wsf[32 + s];
         dl[mt][2 * h + 1] = g_dop * delta[i] * M.gain * lp_sigmoid(raw);
         dl[mt][2 * h] = (t < D.n_feat) ? w * gF[i] * sg * (1.f - sg) : 0.f;
       }
       // ------------------------------ backward sweep ------------------------------
       float d1[2][4][4], d2[2][4][4], a[2][4][4];
-      // last layer: dW (hc^T dY, ho^T dY), db, and d_hc / d_ho
       {
-        __syncwarp();
-        // dY_last tile: 8 valid columns (cols 8..31 of the tile are not read by the NO=1 product)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          *reinterpret_cast<float2*>(ws + B::DY + lp_sw32(16 * mt + g, 2 * t)) = make_float2(lp_tf32_rna(dl[mt][0]), lp_tf32_rna(dl[mt][1]));
-          *reinterpret_cast<float2*>(ws + B::DY + lp_sw32(16 * mt + 8 + g, 2 * t)) = make_float2(lp_tf32_rna(dl[mt][2]), lp_tf32_rna(dl[mt][3]));
-        }
-        __syncwarp();
-        lp_dw<32, 1>(ws + B::AW_LC, ws + B::HC, ws + B::DY, lane);
-        lp_dw<32, 1>(ws + B::AW_LO, ws + B::HO, ws + B::DY, lane);
-        if (lane < 8) {
-          float sacc = 0.f;
-          for (int rr = 0; rr < 32; ++rr) sacc += ws[B::DY + lp_sw32(rr, lane)];
-          db[4] += sacc;
+        for (int mt = 0; mt < 2; ++mt) {  // last-layer gradient tile: columns 2t, 2t+1 (chunk 0)
+          unsigned char* p = wsb + BW::DYL + (2 * mt) * LP_TC_LBO + g * 16 + 4 * t;
+          *reinterpret_cast<unsigned*>(p) = lp_pack_bf16x2(dl[mt][0], dl[mt][1]);
+          *reinterpret_cast<unsigned*>(p + LP_TC_LBO) = lp_pack_bf16x2(dl[mt][2], dl[mt][3]);
         }
         float al[2][1][4];
 #pragma unroll
@@ -727,12 +847,8 @@ __global__ void __launch_bounds__(128) lp_render_bwd_fast_kernel(LpRays R, LpMar
       }
       lp_gate_c(d1, m_hc);
       lp_gate_c(d2, m_ho);
-      // colour hidden layer: dW_c0 += xc^T d_hc', d_xc = d_hc' Wc0^T
-      __syncwarp();
-      lp_store_tile_c(ws + B::DY, d1, g, t);
-      __syncwarp();
-      lp_dw<32, 4>(ws + B::AW_C0, ws + B::XC, ws + B::DY, lane);
-      db[3] += lp_colsum(ws + B::DY, lane);
+      lp_tile_put_c(wsb + BW::DY + 2 * 2048, d1, g, t);  // dY of the colour hidden layer
+      lp_tile_put_c(wsb + BW::DY + 1 * 2048, d2, g, t);  // dY of the opacity hidden layer
       lp_c_to_a_tf32(d1, a);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -747,21 +863,10 @@ __global__ void __launch_bounds__(128) lp_render_bwd_fast_kernel(LpRays R, LpMar
         for (int n = 0; n < 4; ++n)
 #pragma unroll
           for (int i = 0; i < 4; ++i) genc[mt][n][i] += d1[mt][n][i];
-      // opacity hidden layer: dW_o0 += t^T d_ho', d_t = d_xc + d_ho' Wo0^T
-      __syncwarp();
-      lp_store_tile_c(ws + B::DY, d2, g, t);
-      __syncwarp();
-      lp_dw<32, 4>(ws + B::AW_O0, ws + B::TR, ws + B::DY, lane);
-      db[2] += lp_colsum(ws + B::DY, lane);
       lp_c_to_a_tf32(d2, a);
-      lp_dx<4, 4>(smem + L::X_O0, d1, a, lane);  // d1 = d_t
+      lp_dx<4, 4>(smem + L::X_O0, d1, a, lane);  // d1 = d_t = d_xc + d_ho' Wo0^T
       lp_gate_c(d1, m_tr);
-      // trunk layer 1
-      __syncwarp();
-      lp_store_tile_c(ws + B::DY, d1, g, t);
-      __syncwarp();
-      lp_dw<32, 4>(ws + B::AW_T1, ws + B::H1, ws + B::DY, lane);
-      db[1] += lp_colsum(ws + B::DY, lane);
+      lp_tile_put_c(wsb + BW::DY + 0 * 2048, d1, g, t);  // dY of trunk layer 1
       lp_c_to_a_tf32(d1, a);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -771,12 +876,17 @@ __global__ void __launch_bounds__(128) lp_render_bwd_fast_kernel(LpRays R, LpMar
           for (int i = 0; i < 4; ++i) d2[mt][n][i] = 0.f;
       lp_dx<4, 4>(smem + L::X_T1, d2, a, lane);  // d_h1
       lp_gate_c(d2, m_h1);
-      // trunk layer 0
+      lp_tile_put_c(wsb + BW::DY + 3 * 2048, d2, g, t);  // dY of trunk layer 0
+      // hand the operand tiles to the tensor core
+      lp_fence_async_smem();
       __syncwarp();
-      lp_store_tile_c(ws + B::DY, d2, g, t);
-      __syncwarp();
-      lp_dw<C, 4>(ws + B::AW_T0, ws + B::X0, ws + B::DY, lane);
-      db[0] += lp_colsum(ws + B::DY, lane);
+      if (lane == 0) {
+        lp_tc_fence_after();
+        lp_issue_dw(tmem, wsb, 1);
+        lp_tc_commit(bars + warp);
+      }
+      ++iter;
+      // input gradient of the first layer and its scatter into the grid
       lp_c_to_a_tf32(d2, a);
       float dx0[2][C / 8][4];
 #pragma unroll
@@ -786,74 +896,70 @@ __global__ void __launch_bounds__(128) lp_render_bwd_fast_kernel(LpRays R, LpMar
 #pragma unroll
           for (int i = 0; i < 4; ++i) dx0[mt][n][i] = 0.f;
       lp_dx<C / 8, 4>(smem + L::X_T0, dx0, a, lane);
-      // scatter d_x0: row (mt,h) holds channels 16k+4t..+3 in (dx0[mt][2k][2h..], dx0[mt][2k+1][2h..])
+      __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 4; ++i) {  // row i = (mt,h) holds channels 16k+4t..+3 in dx0[mt][2k..2k+1][2h..2h+1]
         const int mt = i >> 1, h = i & 1;
-        float d[C / 4];
 #pragma unroll
-        for (int k = 0; k < C / 16; ++k) {
-          d[4 * k] = dx0[mt][2 * k][2 * h]; d[4 * k + 1] = dx0[mt][2 * k][2 * h + 1];
-          d[4 * k + 2] = dx0[mt][2 * k + 1][2 * h]; d[4 * k + 3] = dx0[mt][2 * k + 1][2 * h + 1];
-        }
-        if (r.active[i]) {
-          const SamplePos p = lp_sample_pos(r, i, step, M);
-          lp_splat_row<C>(G, io.g_grid, r.b[i], p.x, p.y, p.z, p.oob, t, d);
-        }
+        for (int k = 0; k < C / 16; ++k)
+          *reinterpret_cast<float4*>(xs + lp_xs<C>(8 * i + g, 4 * k + t)) =
+              make_float4(dx0[mt][2 * k][2 * h], dx0[mt][2 * k][2 * h + 1], dx0[mt][2 * k + 1][2 * h], dx0[mt][2 * k + 1][2 * h + 1]);
       }
+      __syncwarp();
+      if (me.active) lp_splat_lane<C>(G, io.g_grid, me.b, sx, sy, sz, soob, xs, lane);
     }
     // ray-encoding gradient of this tile
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
-        if (r.active[2 * mt])
-          *reinterpret_cast<float2*>(io.g_enc + (long long)r.ray[2 * mt] * H + 8 * n + 2 * t) = make_float2(genc[mt][n][0], genc[mt][n][1]);
-        if (r.active[2 * mt + 1])
-          *reinterpret_cast<float2*>(io.g_enc + (long long)r.ray[2 * mt + 1] * H + 8 * n + 2 * t) = make_float2(genc[mt][n][2], genc[mt][n][3]);
+        const int r0 = rbase + 16 * mt + g, r1 = r0 + 8;
+        if (r0 < R.n)
+          *reinterpret_cast<float2*>(io.g_enc + (long long)r0 * H + 8 * n + 2 * t) = make_float2(genc[mt][n][0], genc[mt][n][1]);
+        if (r1 < R.n)
+          *reinterpret_cast<float2*>(io.g_enc + (long long)r1 * H + 8 * n + 2 * t) = make_float2(genc[mt][n][2], genc[mt][n][3]);
       }
   }
-  // ---- flush the warp's parameter-gradient accumulators ----
-  __syncwarp();
+  // ---- drain: every warp waits for its last hand-off, then the CTA reads the accumulators ----
+  if (iter > 0) lp_mbar_wait(bars + warp, (iter - 1) & 1);
+  lp_tc_fence_before();
+  __syncthreads();
+  lp_tc_fence_after();
   {
     const LpLayer &t0 = D.trunk.l[0], &t1 = D.trunk.l[1], &o0 = D.opacity.l[0], &o1 = D.opacity.l[1],
                   &c0 = D.color.l[0], &c1 = D.color.l[1];
-    auto flush = [&](const float* acc, const LpLayer& Ly, int mfs) {
-      for (int mf = 0; mf < mfs; ++mf)
-        for (int nn = 0; nn < 4; ++nn) {
-          const float4 v = *reinterpret_cast<const float4*>(acc + ((mf * 4 + nn) * 32 + lane) * 4);
-          float* dst = io.g_params + Ly.w_off;
-          lp_red_add1(dst + (16 * mf + g) * Ly.N + 8 * nn + 2 * t, v.x);
-          lp_red_add1(dst + (16 * mf + g) * Ly.N + 8 * nn + 2 * t + 1, v.y);
-          lp_red_add1(dst + (16 * mf + g + 8) * Ly.N + 8 * nn + 2 * t, v.z);
-          lp_red_add1(dst + (16 * mf + g + 8) * Ly.N + 8 * nn + 2 * t + 1, v.w);
+    float v[32];
+    if (warp < 4) {  // diagonal blocks of A1 x B_j: warp w owns TMEM lanes 32w.. = stack rows 32w..
+      lp_tmem_ld32(tmem, 32 * warp, TM_W + 32 * warp, v);
+      const LpLayer& Ly = warp == 0 ? t1 : (warp == 1 ? o0 : (warp == 2 ? c0 : t0));
+      if (warp < 3 || lane < C) {
+#pragma unroll
+        for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Ly.w_off + lane * Ly.N + n, v[n]);
+      }
+      // last layer (A2 x B_last): rows 0..31 = colour hidden, 32..63 = opacity hidden, 64 = ones
+      if (warp < 3) lp_tmem_ld32(tmem, 32 * warp, TM_L, v);
+      if (warp == 0) {
+        for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.w_off + lane * c1.N + c, v[2 * c]);
+      } else if (warp == 1) {
+        lp_red_add1(io.g_params + o1.w_off + lane, v[1]);
+      } else if (warp == 2) {  // lane 0 <-> stack row 64: bias gradients
+        if (lane == 0) {
+          for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.b_off + c, v[2 * c]);
+          lp_red_add1(io.g_params + o1.b_off, v[1]);
         }
-    };
-    flush(ws + B::AW_T0, t0, C / 16);
-    flush(ws + B::AW_T1, t1, 2);
-    flush(ws + B::AW_O0, o0, 2);
-    flush(ws + B::AW_C0, c0, 2);
-    for (int mf = 0; mf < 2; ++mf) {  // last layer: columns (2t: colour t | 2t+1: opacity for t == 0)
-      const float4 vc = *reinterpret_cast<const float4*>(ws + B::AW_LC + (mf * 32 + lane) * 4);
-      const float4 vo = *reinterpret_cast<const float4*>(ws + B::AW_LO + (mf * 32 + lane) * 4);
-      if (t < D.n_feat) {
-        lp_red_add1(io.g_params + c1.w_off + (16 * mf + g) * c1.N + t, vc.x);
-        lp_red_add1(io.g_params + c1.w_off + (16 * mf + g + 8) * c1.N + t, vc.z);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          lp_tmem_ld32(tmem, 64, TM_B + 32 * j, v);
+          const LpLayer& Lb = j == 0 ? t1 : (j == 1 ? o0 : (j == 2 ? c0 : t0));
+          if (lane == 0)
+            for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Lb.b_off + n, v[n]);
+        }
       }
-      if (t == 0) {
-        lp_red_add1(io.g_params + o1.w_off + (16 * mf + g), vo.y);
-        lp_red_add1(io.g_params + o1.w_off + (16 * mf + g + 8), vo.w);
-      }
-    }
-    lp_red_add1(io.g_params + t0.b_off + lane, db[0]);
-    lp_red_add1(io.g_params + t1.b_off + lane, db[1]);
-    lp_red_add1(io.g_params + o0.b_off + lane, db[2]);
-    lp_red_add1(io.g_params + c0.b_off + lane, db[3]);
-    if (lane < 8) {
-      if (lane & 1) { if (lane == 1) lp_red_add1(io.g_params + o1.b_off, db[4]); }
-      else if ((lane >> 1) < D.n_feat) lp_red_add1(io.g_params + c1.b_off + (lane >> 1), db[4]);
     }
   }
+  lp_tc_fence_before();
+  __syncthreads();
+  if (warp == 0) lp_tmem_dealloc512(tmem);
 }
 
 }  // namespace lpf
@@ -890,7 +996,7 @@ template <int C>
 static int lp_fast_render_forward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, float* out_len,
                                     float* out_nlt, float* out_feat, int feat_stride) {
   const int warps = 8;
-  const size_t bytes = 4ull * (lpf::Lay<C>::FWD_END + warps * 32 * 40);
+  const size_t bytes = 4ull * (lpf::Lay<C>::FWD_END + warps * (32 * 40 + 32 * C));
   if (LP_FAST_SET_SMEM(lpf::lp_render_fwd_fast_kernel<C>, bytes)) return LP_ERR_CUDA;
   const int tiles = (a.R.n + 31) / 32;
   int blocks = (tiles + warps - 1) / warps;
@@ -911,13 +1017,13 @@ static inline bool lp_fast_render_backward_supported(const LpRenderArgs& a) { re
 
 template <int C>
 static int lp_fast_render_backward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
-  // C=16: 4 warps x 38.4 KB + 49.7 KB weight image; C=32: 3 warps (shared-memory budget)
-  const int warps = (C == 16) ? 4 : 3;
-  const size_t bytes = 4ull * (lpf::Lay<C>::END + warps * lpf::BLay<C>::END);
+  // shared memory: weight image + (barriers, TMEM slot) + 22.4 KB of operand tiles per warp
+  const int warps = (C == 16) ? 7 : 6;
+  const size_t bytes = 4ull * (lpf::Lay<C>::END + 32) + (size_t)warps * lpf::BWEnd<C>::value;
   if (LP_FAST_SET_SMEM(lpf::lp_render_bwd_fast_kernel<C>, bytes)) return LP_ERR_CUDA;
   const int tiles = (a.R.n + 31) / 32;
   int blocks = (tiles + warps - 1) / warps;
-  const int max_blocks = lp_fast_num_sms();  // persistent, one CTA per SM
+  const int max_blocks = lp_fast_num_sms();  // persistent, one CTA per SM (it owns the SM's TMEM)
   if (blocks > max_blocks) blocks = max_blocks;
   LP_LAUNCH(lpf::lp_render_bwd_fast_kernel<C>, dim3(blocks), dim3(warps * 32), bytes, st, a.R, a.M, a.D, a.G, params, io);
   return LP_OK;

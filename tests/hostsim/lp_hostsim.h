@@ -17,6 +17,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -33,6 +34,8 @@ struct dim3 {
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct float2 { float x, y; };
+struct uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
 struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
@@ -60,6 +63,7 @@ struct BlockCtx {
   std::barrier<>* bar;
   unsigned char* smem;
   std::vector<WarpCtx>* warps;
+  float* tmem;  // emulated tensor memory: [128 lanes][512 columns]
 };
 
 struct ThreadCtx {
@@ -90,7 +94,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
         }
         unsigned char* smem_aligned =
             reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 63) & ~uintptr_t(63));
-        BlockCtx bctx{&block_bar, smem_aligned, &warps};
+        std::vector<float> tmem(128 * 512, 0.f);
+        BlockCtx bctx{&block_bar, smem_aligned, &warps, tmem.data()};
         std::vector<std::thread> threads;
         threads.reserve(nthreads);
         for (unsigned t = 0; t < nthreads; ++t) {
@@ -216,4 +221,45 @@ static inline void lp_hostsim_mma_m16n8k8(float (&d)[4], const float (&a)[4], co
   }
   w->bar->arrive_and_wait();
   for (int i = 0; i < 4; ++i) d[i] = out[i];
+}
+
+// ---- emulation of the tcgen05 / mbarrier layer of lp_platform.cuh (protocol + layout logic) ----
+// mbarrier: the 64-bit word counts completed phases (every barrier here expects one arrival).
+static inline void lp_mbar_init(unsigned long long* bar, int) { *bar = 0; }
+static inline void lp_mbar_init_fence() {}
+static inline void lp_mbar_wait(unsigned long long* bar, int parity) {
+  while ((int)(std::atomic_ref<unsigned long long>(*bar).load(std::memory_order_acquire) & 1ull) == parity)
+    std::this_thread::yield();
+}
+static inline void lp_fence_async_smem() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void lp_tc_fence_before() {}
+static inline void lp_tc_fence_after() {}
+static inline void lp_tmem_alloc512(unsigned* slot) { if (lp_hostsim::g_ctx->lane == 0) *slot = 0; }
+static inline void lp_tmem_dealloc512(unsigned) {}
+static inline float lp_hs_bf16(const unsigned char* base, int byte_off) {
+  unsigned short h; std::memcpy(&h, base + byte_off, 2);
+  unsigned u = (unsigned)h << 16; float f; std::memcpy(&f, &u, 4); return f;
+}
+// the MMA executes synchronously (program order == issue order, like the in-order tensor pipe)
+static inline void lp_tc_mma_bf16(unsigned tmem_base, int col, const void* a, const void* b, int n, int accumulate) {
+  static std::mutex mu;  // several warps may issue concurrently; the real pipe serialises them
+  std::lock_guard<std::mutex> lk(mu);
+  float* T = lp_hostsim::g_ctx->block->tmem;
+  const unsigned char* A = static_cast<const unsigned char*>(a);
+  const unsigned char* B = static_cast<const unsigned char*>(b);
+  auto off = [](int mn, int k) { return (mn / 8) * 512 + (k / 8) * 128 + (k % 8) * 16 + (mn % 8) * 2; };
+  for (int m = 0; m < 128; ++m)
+    for (int j = 0; j < n; ++j) {
+      float acc = accumulate ? T[m * 512 + tmem_base + col + j] : 0.f;
+      for (int k = 0; k < 16; ++k) acc += lp_hs_bf16(A, off(m, k)) * lp_hs_bf16(B, off(j, k));
+      T[m * 512 + tmem_base + col + j] = acc;
+    }
+}
+static inline void lp_tc_commit(unsigned long long* bar) {
+  std::atomic_ref<unsigned long long>(*bar).fetch_add(1, std::memory_order_release);
+}
+static inline void lp_tmem_ld32(unsigned tmem_base, int lane_base, int col, float (&v)[32]) {
+  const float* T = lp_hostsim::g_ctx->block->tmem;
+  const int row = lane_base + lp_hostsim::g_ctx->lane;
+  for (int j = 0; j < 32; ++j) v[j] = T[row * 512 + tmem_base + col + j];
 }

@@ -30,7 +30,9 @@ def test_hostsim_renderer(lib, name):
     got = render_case(lib, c, "cpu")
     for k, v in got.items():
         assert torch.isfinite(v).all(), (name, k)
-        assert rel_err(v, c["naive_" + k]) < 2e-4, (name, k, rel_err(v, c["naive_" + k]))
+        # tensor-core path (2/2/2 x hidden 32 cases): TF32 backward products, bf16 dW operands
+        tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
+        assert rel_err(v, c["naive_" + k]) < tol, (name, k, rel_err(v, c["naive_" + k]))
 
 
 @pytest.mark.parametrize("name", case_names("splat_"))
