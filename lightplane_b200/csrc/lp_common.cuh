@@ -134,7 +134,8 @@ LP_DEVICE float lp_int_to_randn(int x1, int x2, int seed) {
   return sqrtf(-2.f * logf(u1)) * cosf(6.28318530718f * u2);
 }
 // noise of sample `step` of ray `ray` (fwbw_util.py:66-70; renderer_fw.py:289-296)
-LP_DEVICE float lp_sample_noise(const LpMarch& m, int ray, int step) {
+// (not inlined: logf + large-argument cosf are long code sequences and the callers are unrolled)
+static __device__ __noinline__ float lp_sample_noise(const LpMarch& m, int ray, int step) {
   int tot = m.S + m.S_inf;
   int i1 = (int)((unsigned)ray * (unsigned)tot + (unsigned)step + 1u);
   int i2 = (int)((unsigned)i1 + (unsigned)m.noise_num_rays * (unsigned)tot);

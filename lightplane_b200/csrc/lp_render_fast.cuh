@@ -344,7 +344,7 @@ LP_DEVICE void lp_gather_lane(const LpGridSet& G, int b, float x, float y, float
     const int nt = lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
 #pragma unroll
     for (int tp = 0; tp < 8; ++tp) {
-      if (tp < nt && w[tp] != 0.f) {
+      if (tp < nt) {  // zero-weight taps carry clamped (valid) addresses: load unconditionally, no branches
 #pragma unroll
         for (int k = 0; k < C / 4; ++k) {
           const float4 v = lp_ldg4(G.data + off[tp] + 4 * k);
@@ -433,7 +433,12 @@ __global__ void __launch_bounds__(256, 2) lp_render_fwd_fast_kernel(LpRays R, Lp
   const int num_tiles = (R.n + 31) / 32;
   const int tot = M.S + M.S_inf;
 
-  for (int tile = blockIdx.x * nwarps + warp; tile < num_tiles; tile += gridDim.x * nwarps) {
+  // Every warp of every CTA runs the same number of tiles (surplus tiles are all-inactive rays), so
+  // the per-step CTA barrier below is well formed; it keeps the warps on the same instruction-cache
+  // lines -- the unrolled step body is ~100 KB of code and otherwise every warp streams it separately.
+  const int tiles_per_warp = (num_tiles + gridDim.x * nwarps - 1) / (gridDim.x * nwarps);
+  for (int it = 0; it < tiles_per_warp; ++it) {
+    const int tile = (it * gridDim.x + blockIdx.x) * nwarps + warp;
     const int rbase = tile * 32;
     const Ray1 me = lp_load_ray1(R, rbase + lane, G.g[0].B);
     float rnear[4], rfar[4];
@@ -452,6 +457,7 @@ __global__ void __launch_bounds__(256, 2) lp_render_fwd_fast_kernel(LpRays R, Lp
     float nlt[4] = {0.f, 0.f, 0.f, 0.f}, T[4] = {1.f, 1.f, 1.f, 1.f}, accum[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (int step = 0; step < tot; ++step) {
+      __syncthreads();
       const Sched sc = lp_sched(step, M);
       float xa[4][C / 4], depth[4], delta[4];
       {
@@ -693,7 +699,9 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
   const int tot = M.S + M.S_inf;
   int iter = 0;  // number of operand hand-offs this warp has made
 
-  for (int tile = blockIdx.x * nwarps + warp; tile < num_tiles; tile += gridDim.x * nwarps) {
+  const int tiles_per_warp = (num_tiles + gridDim.x * nwarps - 1) / (gridDim.x * nwarps);  // see forward kernel
+  for (int it = 0; it < tiles_per_warp; ++it) {
+    const int tile = (it * gridDim.x + blockIdx.x) * nwarps + warp;
     const int rbase = tile * 32;
     const Ray1 me = lp_load_ray1(R, rbase + lane, G.g[0].B);
     float rnear[4], rfar[4];
@@ -728,6 +736,7 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
         for (int i = 0; i < 4; ++i) genc[mt][n][i] = 0.f;
 
     for (int step = 0; step < tot; ++step) {
+      __syncthreads();
       // operand tiles of the previous hand-off must have been consumed by the tensor core
       if (iter > 0) lp_mbar_wait(bars + warp, (iter - 1) & 1);
       // ------------------------------ forward recompute ------------------------------

@@ -26,6 +26,7 @@
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
+#define __noinline__ __attribute__((noinline))
 #define __align__(n) __attribute__((aligned(n)))
 
 struct uint3 { unsigned x, y, z; };
