@@ -1,0 +1,140 @@
+"""The reference's own parity sweeps (tests/test_renderer_with_autograd.py:35-56,
+tests/test_splatter_with_autograd.py:38-53), re-run against the oracle on seeded inputs:
+every optional feature x voxel/triplane x layer counts x ray counts that do not divide the tile."""
+import itertools
+
+import pytest
+import torch
+
+from _golden import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _rays(n, batch, enc_dim, seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(n, 3, generator=g) / 3
+    d = -o + 0.1 * torch.randn(n, 3, generator=g)
+    near = torch.randn(n, generator=g) * 0.1 + 0.1
+    far = torch.randn(n, generator=g).abs() * 0.1 + 3.0
+    gi = torch.randint(0, batch, (n,), generator=g)
+    enc = torch.randn(n, enc_dim, generator=g)
+    return [t.to(dev) for t in (d, o, gi, near, far, enc)]
+
+
+def _shapes(size, triplane):
+    if not triplane:
+        return [list(size)]
+    return [[size[0]] + [1 if j == i else size[1 + j] for j in range(3)] + [size[4]] for i in range(3)]
+
+
+SWEEP = [
+    # (triplane, layers t/o/c, hidden, n_rays, inf, gain, mask, contract, sigma, scaffold, color_grid)
+    (False, (2, 2, 2), 32, 128, 0, 1.0, False, False, 0.0, False, False),
+    (True, (2, 2, 2), 32, 131, 5, 3.0, False, False, 0.0, False, False),   # fast path, ragged tile, inf
+    (True, (2, 2, 2), 32, 64, 0, 1.0, True, False, 1.0, False, False),     # fast path + mask + noise
+    (True, (2, 2, 2), 32, 64, 3, 1.0, False, True, 0.0, False, False),     # fast path + contraction
+    (True, (4, 2, 4), 32, 3, 11, 1.0, True, False, 0.0, False, False),     # generic: deep MLPs, 3 rays
+    (False, (2, 4, 2), 32, 128, 0, 3.0, False, False, 1.0, True, False),   # scaffold + noise
+    (False, (1, 1, 1), 16, 35, 0, 1.0, False, True, 0.0, True, False),
+    (True, (0, 2, 2), 32, 128, 4, 1.0, False, False, 0.0, False, True),    # colour grid (relu field)
+    (False, (0, 4, 1), 16, 48, 0, 2.0, True, False, 0.0, True, True),
+]
+
+
+@pytest.mark.parametrize("cfg", SWEEP)
+def test_renderer_sweep_vs_oracle(cfg):
+    import lightplane_b200 as lp
+    from oracle import lightplane_oracle as O
+
+    triplane, (nt, no, nc), hid, n, inf, gain, mask, contract, sigma, use_scaf, cgrid = cfg
+    dev = "cuda"
+    torch.manual_seed(hash(cfg) % 1000)
+    size = (3, 16, 12, 8, 16)
+    C, S = size[4], 16
+    shapes = _shapes(size, triplane)
+    dp = lp.init_decoder_params(dev, no, nt, nc, input_chn=C, hidden_chn=hid, color_chn=3,
+                                opacity_init_bias=-1.0, use_separate_color_grid=cgrid)
+    dp.mlp_params = (dp.mlp_params + 0.03 * torch.randn_like(dp.mlp_params)).requires_grad_(True)
+    enc_dim = C if cgrid else hid
+    d, o, gi, nr, fr, enc = _rays(n, size[0], enc_dim, 7, dev)
+    enc.requires_grad_(True)
+    grids = [torch.randn(s, device=dev).requires_grad_(True) for s in shapes]
+    cgrids = [torch.randn(s, device=dev).requires_grad_(True) for s in shapes] if cgrid else None
+    scaffold = (torch.randn(size[0], 6, 5, 7, device=dev) > -0.3).float() if use_scaf else None
+    rays = lp.Rays(directions=d, origins=o, grid_idx=gi, near=nr, far=fr, encoding=enc)
+    kw = dict(num_samples=S, gain=gain, num_samples_inf=inf, mask_out_of_bounds_samples=mask,
+              contract_coords=contract, inject_noise_sigma=sigma, inject_noise_seed=13)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        outs = lp.lightplane_renderer(rays, grids, dp, scaffold=scaffold, color_grid=cgrids, **kw)
+    cot = [torch.randn_like(v) for v in outs]
+    leaves = grids + [dp.mlp_params, enc] + (cgrids or [])
+    grads = torch.autograd.grad(sum((c * v).sum() for c, v in zip(cot, outs)), leaves)
+
+    f = lambda t: t.detach().double().cpu()
+    og = f(torch.cat([g.reshape(-1, C) for g in grids], 0)).requires_grad_(True)
+    oc = f(torch.cat([g.reshape(-1, C) for g in cgrids], 0)).requires_grad_(True) if cgrid else None
+    om, oe = f(dp.mlp_params).requires_grad_(True), f(enc).requires_grad_(True)
+    nh = [[int(v) for v in t.tolist()] for t in (dp.n_hidden_trunk, dp.n_hidden_opacity, dp.n_hidden_color)]
+    oo = O.render(f(d), f(o), gi.cpu(), f(nr), f(fr), oe, og, shapes, om, nh[0], nh[1], nh[2],
+                  scaffold=f(scaffold) if use_scaf else None, color_grid_flat=oc,
+                  color_grid_sizes=shapes if cgrid else None, **kw)
+    oo = (oo[0], oo[1], oo[2][:, :3])
+    oleaves = [og, om, oe] + ([oc] if cgrid else [])
+    ograds = torch.autograd.grad(sum((f(c) * v).sum() for c, v in zip(cot, oo)), oleaves)
+    fast = (nt, no, nc) == (2, 2, 2) and hid == 32 and not use_scaf and not cgrid
+    for a, b, nm in zip(outs, oo, ("ray_length", "nlt", "features")):
+        assert rel_err(a, b) < 2e-4, (cfg, nm, rel_err(a, b))
+    ng = len(grids)
+    got = [torch.cat([g.reshape(-1, C) for g in grads[:ng]], 0), grads[ng], grads[ng + 1]]
+    if cgrid:
+        got.append(torch.cat([g.reshape(-1, C) for g in grads[ng + 2:]], 0))
+    for a, b, nm in zip(got, ograds, ("g_grid", "g_mlp", "g_enc", "g_color_grid")):
+        tol = (6e-3 if nm == "g_mlp" else 1e-3) if fast else 2e-4
+        assert rel_err(a, b) < tol, (cfg, nm, rel_err(a, b))
+
+
+SPLAT_SWEEP = list(itertools.product([False, True], [False, True], [1, 128], [False, True], [None, (3, 64), (4, 32)]))
+
+
+@pytest.mark.parametrize("contract,mask,n,triplane,mlp", SPLAT_SWEEP)
+def test_splatter_sweep_vs_oracle(contract, mask, n, triplane, mlp):
+    import lightplane_b200 as lp
+    from oracle import lightplane_oracle as O
+
+    dev = "cuda"
+    torch.manual_seed(3)
+    out_size, in_size = (2, 16, 12, 8, 32), (2, 10, 14, 16, 32)
+    S, Sinf, C = 16, 11, 32
+    feat_dim = C if mlp is None else 32
+    shapes, in_shapes = _shapes(out_size, triplane), _shapes(in_size, triplane)
+    d, o, gi, nr, fr, _ = _rays(n, 2, 4, 5, dev)
+    feat = torch.rand(n, feat_dim, device=dev, requires_grad=True)
+    rays = lp.Rays(directions=d, origins=o, grid_idx=gi, near=nr, far=fr, encoding=feat)
+    kw = dict(num_samples=S, num_samples_inf=Sinf, mask_out_of_bounds_samples=mask, contract_coords=contract)
+    f = lambda t: t.detach().double().cpu()
+    ofeat = f(feat).requires_grad_(True)
+    if mlp is None:
+        out = lp.lightplane_splatter(rays, [tuple(s) for s in shapes], return_list=False, **kw)
+        leaves, okw, oleaves = [feat], {}, [ofeat]
+    else:
+        sp = lp.init_splatter_params(dev, n_layers=mlp[0], input_chn=feat_dim, hidden_chn=mlp[1], out_chn=C)
+        sp.mlp_params.requires_grad_(True)
+        ing = [torch.randn(s, device=dev).requires_grad_(True) for s in in_shapes]
+        out = lp.lightplane_mlp_splatter(rays, [tuple(s) for s in shapes], sp, ing, return_list=False, **kw)
+        leaves = [feat, sp.mlp_params] + ing
+        om = f(sp.mlp_params).requires_grad_(True)
+        oi = f(torch.cat([g.reshape(-1, feat_dim) for g in ing], 0)).requires_grad_(True)
+        okw = dict(mlp_params=om, mlp_dims=[int(v) for v in sp.n_hidden.tolist()], input_grid_flat=oi, input_sizes=in_shapes)
+        oleaves = [ofeat, om, oi]
+    cot = torch.randn_like(out)
+    grads = torch.autograd.grad((out * cot).sum(), leaves)
+    oout = O.splat(f(d), f(o), gi.cpu(), f(nr), f(fr), ofeat, shapes, **kw, **okw)
+    ograds = torch.autograd.grad((oout * f(cot)).sum(), oleaves)
+    assert rel_err(out, oout) < 2e-4
+    got = [grads[0]] + ([grads[1], torch.cat([g.reshape(-1, feat_dim) for g in grads[2:]], 0)] if mlp else [])
+    for a, b in zip(got, ograds):
+        assert rel_err(a, b) < 2e-4, rel_err(a, b)
