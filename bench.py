@@ -192,7 +192,14 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    # non-default workloads (e.g. BASELINE.json configs[4]: --samples 256 --plane 128 --grid-chn 32)
+    ap.add_argument("--samples", type=int, default=S)
+    ap.add_argument("--plane", type=int, default=PLANE)
+    ap.add_argument("--grid-chn", type=int, default=C)
     args = ap.parse_args()
+    globals().update(S=args.samples, PLANE=args.plane, C=args.grid_chn)
+    globals().update(MAC_FWD=C * H + H * H + (H * H + H) + (H * H + H * COLOR))
+    globals().update(FLOP_FWD_PER_SAMPLE=2 * MAC_FWD, FLOP_BWD_PER_SAMPLE=4 * MAC_FWD)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":

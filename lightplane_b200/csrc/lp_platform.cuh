@@ -32,11 +32,35 @@ LP_DEVICE void lp_red_add4(float* addr, float a, float b, float c, float d) {
 #endif
 }
 
+// predicated form (no branch): the reduction is issued only when `pred` holds
+LP_DEVICE void lp_red_add4_if(bool pred, float* addr, float a, float b, float c, float d) {
+#if defined(LP_HOSTSIM)
+  if (pred) { atomicAdd(addr + 0, a); atomicAdd(addr + 1, b); atomicAdd(addr + 2, c); atomicAdd(addr + 3, d); }
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}\n" ::"l"(addr),
+      "f"(a), "f"(b), "f"(c), "f"(d), "r"((int)pred)
+      : "memory");
+#endif
+}
+
 LP_DEVICE void lp_red_add1(float* addr, float a) {
 #if defined(LP_HOSTSIM)
   atomicAdd(addr, a);
 #else
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+#endif
+}
+
+// 16-byte read-only load that does not allocate in L1: the backward kernel's L1 is ~29 KB (the rest
+// of the 256 KB is shared memory) and is better spent on the per-ray encodings than on grid rows
+LP_DEVICE float4 lp_ldg4_stream(const float* p) {
+#if defined(LP_HOSTSIM)
+  return make_float4(p[0], p[1], p[2], p[3]);
+#else
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
 #endif
 }
 
@@ -148,6 +172,21 @@ LP_DEVICE void lp_tc_mma_bf16(unsigned tmem_base, int col, const void* a, const 
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_base + (unsigned)col),
       "l"(lp_tc_desc(a)), "l"(lp_tc_desc(b)), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same, with operands addressed as byte offsets from one 16-byte aligned shared-memory base whose
+// descriptor low word `base_lo` (= lp_tc_desc_lo(base)) is computed once: ~4 instructions per MMA.
+LP_DEVICE unsigned lp_tc_desc_lo(const void* smem_ptr) {
+  return ((lp_smem_u32(smem_ptr) >> 4) & 0x3FFF) | ((unsigned)(LP_TC_LBO >> 4) << 16);
+}
+LP_DEVICE void lp_tc_mma_bf16_off(unsigned tmem_base, int col, unsigned base_lo, const void*, int a_off, int b_off,
+                                   int n, int accumulate) {
+  const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(n >> 3) << 17) | (8u << 24);
+  const unsigned hi = (unsigned)(LP_TC_SBO >> 4) | (1u << 14);  // SBO at bits 32..45, version 1 at bit 46
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_base + (unsigned)col),
+      "r"(base_lo + (unsigned)(a_off >> 4)), "r"(base_lo + (unsigned)(b_off >> 4)), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 LP_DEVICE void lp_tc_commit(unsigned long long* bar) {

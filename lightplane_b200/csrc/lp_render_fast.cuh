@@ -23,6 +23,9 @@
 namespace lpf {
 
 constexpr int H = 32;
+#ifndef LP_ALIGN_MASK
+#define LP_ALIGN_MASK 0  // re-align the warps of a CTA every (mask+1) steps (I-cache sharing vs barrier stalls)
+#endif
 
 template <int C>
 struct Lay {
@@ -333,7 +336,7 @@ LP_DEVICE int lp_xs(int r, int k) {
 }
 
 // The ray-owner lane samples all C channels of its sample point and drops them into the tile.
-template <int C>
+template <int C, bool STREAM = false>
 LP_DEVICE void lp_gather_lane(const LpGridSet& G, int b, float x, float y, float z, float oob, float* xs, int lane) {
   float acc[C];
 #pragma unroll
@@ -347,7 +350,7 @@ LP_DEVICE void lp_gather_lane(const LpGridSet& G, int b, float x, float y, float
       if (tp < nt) {  // zero-weight taps carry clamped (valid) addresses: load unconditionally, no branches
 #pragma unroll
         for (int k = 0; k < C / 4; ++k) {
-          const float4 v = lp_ldg4(G.data + off[tp] + 4 * k);
+          const float4 v = STREAM ? lp_ldg4_stream(G.data + off[tp] + 4 * k) : lp_ldg4(G.data + off[tp] + 4 * k);
           acc[4 * k] = fmaf(w[tp], v.x, acc[4 * k]); acc[4 * k + 1] = fmaf(w[tp], v.y, acc[4 * k + 1]);
           acc[4 * k + 2] = fmaf(w[tp], v.z, acc[4 * k + 2]); acc[4 * k + 3] = fmaf(w[tp], v.w, acc[4 * k + 3]);
         }
@@ -387,11 +390,12 @@ LP_DEVICE void lp_splat_lane(const LpGridSet& G, float* grad, int b, float x, fl
     const int nt = lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
 #pragma unroll
     for (int tp = 0; tp < 8; ++tp) {
-      if (tp < nt && w[tp] != 0.f) {
+      if (tp < nt) {
+        const bool on = w[tp] != 0.f;  // taps outside the grid: no atomic traffic
 #pragma unroll
         for (int k = 0; k < C / 4; ++k)
-          lp_red_add4(grad + off[tp] + 4 * k, w[tp] * d[4 * k], w[tp] * d[4 * k + 1], w[tp] * d[4 * k + 2],
-                      w[tp] * d[4 * k + 3]);
+          lp_red_add4_if(on, grad + off[tp] + 4 * k, w[tp] * d[4 * k], w[tp] * d[4 * k + 1], w[tp] * d[4 * k + 2],
+                         w[tp] * d[4 * k + 3]);
       }
     }
   }
@@ -457,7 +461,7 @@ __global__ void __launch_bounds__(256, 2) lp_render_fwd_fast_kernel(LpRays R, Lp
     float nlt[4] = {0.f, 0.f, 0.f, 0.f}, T[4] = {1.f, 1.f, 1.f, 1.f}, accum[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (int step = 0; step < tot; ++step) {
-      __syncthreads();
+      if ((step & LP_ALIGN_MASK) == 0) __syncthreads();
       const Sched sc = lp_sched(step, M);
       float xa[4][C / 4], depth[4], delta[4];
       {
@@ -640,20 +644,26 @@ struct BWEnd { static constexpr int value = BW::XS + 32 * C * 4; };
 // TMEM columns
 constexpr int TM_W = 0, TM_B = 128, TM_L = 256;
 
-// lane 0 of a warp: reduce this warp's 32 samples into the CTA's TMEM accumulators
-LP_DEVICE void lp_issue_dw(unsigned tmem, const unsigned char* wsb, int accumulate) {
+// lane 0 of a warp: reduce this warp's 32 samples into the CTA's TMEM accumulators.
+// C == 16 leaves stack rows 112..127 of A1 free: the row of ones lives there (row 112) and the bias
+// gradients come out of the A1 products; C == 32 fills A1, so the ones sit in A2 (row 64) and four
+// more products A2 x B_j are needed.
+template <int C>
+LP_DEVICE void lp_issue_dw(unsigned tmem, unsigned base_lo, const unsigned char* wsb, int accumulate) {
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
-      lp_tc_mma_bf16(tmem, TM_W + 32 * j, wsb + BW::A1 + ks * 2 * LP_TC_LBO, wsb + BW::DY + j * 2048 + ks * 2 * LP_TC_LBO, 32,
-                     accumulate | ks);
-      lp_tc_mma_bf16(tmem, TM_B + 32 * j, wsb + BW::A2 + ks * 2 * LP_TC_LBO, wsb + BW::DY + j * 2048 + ks * 2 * LP_TC_LBO, 32,
-                     accumulate | ks);
+      lp_tc_mma_bf16_off(tmem, TM_W + 32 * j, base_lo, wsb, BW::A1 + ks * 2 * LP_TC_LBO,
+                         BW::DY + j * 2048 + ks * 2 * LP_TC_LBO, 32, accumulate | ks);
+      if (C != 16)
+        lp_tc_mma_bf16_off(tmem, TM_B + 32 * j, base_lo, wsb, BW::A2 + ks * 2 * LP_TC_LBO,
+                           BW::DY + j * 2048 + ks * 2 * LP_TC_LBO, 32, accumulate | ks);
     }
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks)
-    lp_tc_mma_bf16(tmem, TM_L, wsb + BW::A2 + ks * 2 * LP_TC_LBO, wsb + BW::DYL + ks * 2 * LP_TC_LBO, 16, accumulate | ks);
+    lp_tc_mma_bf16_off(tmem, TM_L, base_lo, wsb, BW::A2 + ks * 2 * LP_TC_LBO, BW::DYL + ks * 2 * LP_TC_LBO, 16,
+                       accumulate | ks);
 }
 
 template <int C>
@@ -672,10 +682,13 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
   lp_build_weights<C, true>(smem, params, D);
   for (int e = lane; e < BW::RAYS / 4; e += 32) reinterpret_cast<unsigned*>(wsb)[e] = 0u;  // zero all operand tiles
   __syncwarp();
-  if (lane < 32) {  // the row of ones of A2 (stack row 64 = chunk 8, element 0), bf16 1.0 = 0x3F80
+  {  // rows of ones (bf16 1.0 = 0x3F80): A2 stack row 64 (chunk 8) and, for C == 16, A1 stack row 112 (chunk 14)
     const int s = lane;
     *reinterpret_cast<unsigned short*>(wsb + BW::A2 + 8 * LP_TC_SBO + (s >> 3) * LP_TC_LBO + (s & 7) * 16) = 0x3F80;
+    if (C == 16)
+      *reinterpret_cast<unsigned short*>(wsb + BW::A1 + 14 * LP_TC_SBO + (s >> 3) * LP_TC_LBO + (s & 7) * 16) = 0x3F80;
   }
+  const unsigned base_lo = lp_tc_desc_lo(wsb);
   if (threadIdx.x == 0) {
     for (int w = 0; w <= nwarps; ++w) lp_mbar_init(bars + w, 1);
     lp_mbar_init_fence();
@@ -687,7 +700,7 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
   lp_tc_fence_after();
   const unsigned tmem = *tmem_slot;
   if (threadIdx.x == 0) {  // zero the accumulators: D = 0 * 0 with accumulate off (dY tiles are zero)
-    lp_issue_dw(tmem, wsb, 0);
+    lp_issue_dw<32>(tmem, base_lo, wsb, 0);  // <32>: clears every column range
     lp_tc_commit(bars + nwarps);
   }
   lp_mbar_wait(bars + nwarps, 0);
@@ -736,7 +749,7 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
         for (int i = 0; i < 4; ++i) genc[mt][n][i] = 0.f;
 
     for (int step = 0; step < tot; ++step) {
-      __syncthreads();
+      if ((step & LP_ALIGN_MASK) == 0) __syncthreads();
       // operand tiles of the previous hand-off must have been consumed by the tensor core
       if (iter > 0) lp_mbar_wait(bars + warp, (iter - 1) & 1);
       // ------------------------------ forward recompute ------------------------------
@@ -754,7 +767,9 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
           if (M.contract) lp_contract(sx, sy, sz);
           soob = M.mask_oob ? lp_in_bounds(sx, sy, sz) : 1.f;
           __syncwarp();
-          lp_gather_lane<C>(G, me.b, sx, sy, sz, soob, xs, lane);
+#ifndef LP_ABL_NO_GATHER
+          lp_gather_lane<C, true>(G, me.b, sx, sy, sz, soob, xs, lane);
+#endif
           __syncwarp();
           lp_read_rows<C>(xs, g, t, xa);
         }
@@ -796,8 +811,12 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
 #pragma unroll
           for (int n = 0; n < 4; ++n) {
             const int q0 = min(rbase + 16 * mt + g, R.n - 1), q1 = min(rbase + 16 * mt + 8 + g, R.n - 1);
+#ifdef LP_ABL_NO_ENC
+            const float2 e0 = make_float2(0.1f * q0, 0.2f), e1 = make_float2(0.3f, 0.1f * q1);
+#else
             const float2 e0 = __ldg(reinterpret_cast<const float2*>(R.enc + (long long)q0 * H + 8 * n + 2 * t));
             const float2 e1 = __ldg(reinterpret_cast<const float2*>(R.enc + (long long)q1 * H + 8 * n + 2 * t));
+#endif
             tr[mt][n][0] += e0.x; tr[mt][n][2] += e0.y; tr[mt][n][1] += e1.x; tr[mt][n][3] += e1.y;
           }
         lp_tile_put_a(wsb + BW::A1, 8, tr, g, t);
@@ -889,12 +908,14 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
       // hand the operand tiles to the tensor core
       lp_fence_async_smem();
       __syncwarp();
+#ifndef LP_ABL_NO_DW
       if (lane == 0) {
         lp_tc_fence_after();
-        lp_issue_dw(tmem, wsb, 1);
+        lp_issue_dw<C>(tmem, base_lo, wsb, 1);
         lp_tc_commit(bars + warp);
       }
       ++iter;
+#endif
       // input gradient of the first layer and its scatter into the grid
       lp_c_to_a_tf32(d2, a);
       float dx0[2][C / 8][4];
@@ -915,7 +936,9 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
               make_float4(dx0[mt][2 * k][2 * h], dx0[mt][2 * k][2 * h + 1], dx0[mt][2 * k + 1][2 * h], dx0[mt][2 * k + 1][2 * h + 1]);
       }
       __syncwarp();
+#ifndef LP_ABL_NO_SPLAT
       if (me.active) lp_splat_lane<C>(G, io.g_grid, me.b, sx, sy, sz, soob, xs, lane);
+#endif
     }
     // ray-encoding gradient of this tile
 #pragma unroll
@@ -951,16 +974,20 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
         for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.w_off + lane * c1.N + c, v[2 * c]);
       } else if (warp == 1) {
         lp_red_add1(io.g_params + o1.w_off + lane, v[1]);
-      } else if (warp == 2) {  // lane 0 <-> stack row 64: bias gradients
+      } else if (warp == 2) {  // lane 0 <-> stack row 64 of A2: last-layer bias gradients
         if (lane == 0) {
           for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.b_off + c, v[2 * c]);
           lp_red_add1(io.g_params + o1.b_off, v[1]);
         }
+      }
+      // bias gradients of the four 32-wide layers = the row of ones times B_j
+      const int ones_warp = (C == 16) ? 3 : 2, ones_lane = (C == 16) ? 16 : 0;
+      if (warp == ones_warp) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          lp_tmem_ld32(tmem, 64, TM_B + 32 * j, v);
+          lp_tmem_ld32(tmem, 32 * ones_warp, ((C == 16) ? TM_W : TM_B) + 32 * j, v);
           const LpLayer& Lb = j == 0 ? t1 : (j == 1 ? o0 : (j == 2 ? c0 : t0));
-          if (lane == 0)
+          if (lane == ones_lane)
             for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Lb.b_off + n, v[n]);
         }
       }

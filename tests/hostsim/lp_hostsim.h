@@ -264,3 +264,10 @@ static inline void lp_tmem_ld32(unsigned tmem_base, int lane_base, int col, floa
   const int row = lane_base + lp_hostsim::g_ctx->lane;
   for (int j = 0; j < 32; ++j) v[j] = T[row * 512 + tmem_base + col + j];
 }
+
+static inline unsigned lp_tc_desc_lo(const void*) { return 0; }
+static inline void lp_tc_mma_bf16_off(unsigned tmem_base, int col, unsigned, const void* base, int a_off, int b_off, int n,
+                                      int accumulate) {
+  const unsigned char* b = static_cast<const unsigned char*>(base);
+  lp_tc_mma_bf16(tmem_base, col, b + a_off, b + b_off, n, accumulate);
+}
