@@ -23,6 +23,9 @@
 namespace lpf {
 
 constexpr int H = 32;
+#ifndef LP_GATHER_STREAM
+#define LP_GATHER_STREAM 0  // backward gathers bypass L1 allocation (keeps the ray encodings L1-resident)
+#endif
 #ifndef LP_ALIGN_MASK
 #define LP_ALIGN_MASK 0  // re-align the warps of a CTA every (mask+1) steps (I-cache sharing vs barrier stalls)
 #endif
@@ -350,7 +353,7 @@ LP_DEVICE void lp_gather_lane(const LpGridSet& G, int b, float x, float y, float
       if (tp < nt) {  // zero-weight taps carry clamped (valid) addresses: load unconditionally, no branches
 #pragma unroll
         for (int k = 0; k < C / 4; ++k) {
-          const float4 v = STREAM ? lp_ldg4_stream(G.data + off[tp] + 4 * k) : lp_ldg4(G.data + off[tp] + 4 * k);
+          const float4 v = (STREAM && LP_GATHER_STREAM) ? lp_ldg4_stream(G.data + off[tp] + 4 * k) : lp_ldg4(G.data + off[tp] + 4 * k);
           acc[4 * k] = fmaf(w[tp], v.x, acc[4 * k]); acc[4 * k + 1] = fmaf(w[tp], v.y, acc[4 * k + 1]);
           acc[4 * k + 2] = fmaf(w[tp], v.z, acc[4 * k + 2]); acc[4 * k + 3] = fmaf(w[tp], v.w, acc[4 * k + 3]);
         }
@@ -630,39 +633,50 @@ LP_DEVICE void lp_tile_put_c(unsigned char* tile, const float (&c)[2][4][4], int
     }
 }
 
-// per-warp shared memory of the backward kernel (bytes)
+// per-warp shared memory of the backward kernel (bytes).  A1 stacks the left operands of the four
+// 32-wide layers: chunks 0-3 = h1, 4-7 = trunk output, 8.. = grid features x0, then one chunk whose
+// first row is all ones (bias gradients).  The tensor core always reads a 16-chunk (M = 128) window;
+// the rows behind the used ones are whatever follows in the warp's region and are never read back.
+template <int C>
 struct BW {
-  static constexpr int A1 = 0;                 // 16 chunks x 512 B
-  static constexpr int A2 = A1 + 8192;         // 9 chunks used; the MMA's 16-chunk window runs on into
-  static constexpr int DY = A2 + 9 * 512;      //   the gradient tiles behind it (finite data, rows unused)
-  static constexpr int DYL = DY + 4 * 2048;    // last-layer gradient tile [32 samples][16]
-  static constexpr int RAYS = DYL + 1024;      // fp32 [3][32]: total, g_nlt, g_len per ray
-  static constexpr int XS = RAYS + 384;        // fp32 [32][C] transfer tile (ray-owner <-> quad rows)
+  static constexpr int ONES = 8 + C / 8;          // chunk holding the row of ones = stack row 64 + C
+  static constexpr int A1 = 0;
+  static constexpr int A2 = A1 + (ONES + 1) * 512;  // colour hidden | opacity hidden | ones : 9 chunks
+  static constexpr int DY = A2 + 9 * 512;         // four gradient tiles [32 samples][32]
+  static constexpr int DYL = DY + 4 * 2048;       // last-layer gradient tile [32 samples][16]
+  static constexpr int RAYS = DYL + 1024;         // fp32 [3][32]: total, g_nlt, g_len per ray
+  static constexpr int XS = RAYS + 384;           // fp32 [32][C] transfer tile (ray-owner <-> quad rows)
+  static constexpr int END = XS + 32 * C * 4;
+  static_assert(A2 + 16 * 512 <= END, "operand window leaves the warp's region");
 };
 template <int C>
-struct BWEnd { static constexpr int value = BW::XS + 32 * C * 4; };
-// TMEM columns
-constexpr int TM_W = 0, TM_B = 128, TM_L = 256;
+struct BWEnd { static constexpr int value = BW<C>::END; };
+// TMEM columns: four A1 x dY_j products, the per-tile encoding product, the last-layer product
+constexpr int TM_W = 0, TM_E = 128, TM_L = 160;
 
-// lane 0 of a warp: reduce this warp's 32 samples into the CTA's TMEM accumulators.
-// C == 16 leaves stack rows 112..127 of A1 free: the row of ones lives there (row 112) and the bias
-// gradients come out of the A1 products; C == 32 fills A1, so the ones sit in A2 (row 64) and four
-// more products A2 x B_j are needed.
+// lane 0 of a warp: reduce this warp's 32 samples into the CTA's TMEM accumulators (10 MMAs)
 template <int C>
 LP_DEVICE void lp_issue_dw(unsigned tmem, unsigned base_lo, const unsigned char* wsb, int accumulate) {
+  using B = BW<C>;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      lp_tc_mma_bf16_off(tmem, TM_W + 32 * j, base_lo, wsb, BW::A1 + ks * 2 * LP_TC_LBO,
-                         BW::DY + j * 2048 + ks * 2 * LP_TC_LBO, 32, accumulate | ks);
-      if (C != 16)
-        lp_tc_mma_bf16_off(tmem, TM_B + 32 * j, base_lo, wsb, BW::A2 + ks * 2 * LP_TC_LBO,
-                           BW::DY + j * 2048 + ks * 2 * LP_TC_LBO, 32, accumulate | ks);
-    }
+    for (int ks = 0; ks < 2; ++ks)
+      lp_tc_mma_bf16_off(tmem, TM_W + 32 * j, base_lo, wsb, B::A1 + ks * 2 * LP_TC_LBO,
+                         B::DY + j * 2048 + ks * 2 * LP_TC_LBO, 32, accumulate | ks);
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks)
-    lp_tc_mma_bf16_off(tmem, TM_L, base_lo, wsb, BW::A2 + ks * 2 * LP_TC_LBO, BW::DYL + ks * 2 * LP_TC_LBO, 16,
+    lp_tc_mma_bf16_off(tmem, TM_L, base_lo, wsb, B::A2 + ks * 2 * LP_TC_LBO, B::DYL + ks * 2 * LP_TC_LBO, 16,
+                       accumulate | ks);
+}
+// once per ray tile: encoding^T x (sum over steps of the colour-hidden gradient), operands in A1
+// chunks 0-3 and gradient tile 2
+template <int C>
+LP_DEVICE void lp_issue_enc(unsigned tmem, unsigned base_lo, const unsigned char* wsb, int accumulate) {
+  using B = BW<C>;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+    lp_tc_mma_bf16_off(tmem, TM_E, base_lo, wsb, B::A1 + ks * 2 * LP_TC_LBO, B::DY + 2 * 2048 + ks * 2 * LP_TC_LBO, 32,
                        accumulate | ks);
 }
 
@@ -670,23 +684,23 @@ template <int C>
 __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
                                                                 const float* __restrict__ params, LpBwdIo io) {
   using L = Lay<C>;
+  using B = BW<C>;
   LP_DYN_SMEM(float, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + L::END);  // [nwarps] + 1
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 9);
   unsigned char* wsb = reinterpret_cast<unsigned char*>(smem + L::END + 32) + warp * BWEnd<C>::value;
-  float* wsf = reinterpret_cast<float*>(wsb + BW::RAYS);
-  float* xs = reinterpret_cast<float*>(wsb + BW::XS);
+  float* wsf = reinterpret_cast<float*>(wsb + B::RAYS);
+  float* xs = reinterpret_cast<float*>(wsb + B::XS);
 
   lp_build_weights<C, true>(smem, params, D);
-  for (int e = lane; e < BW::RAYS / 4; e += 32) reinterpret_cast<unsigned*>(wsb)[e] = 0u;  // zero all operand tiles
+  for (int e = lane; e < B::RAYS / 4; e += 32) reinterpret_cast<unsigned*>(wsb)[e] = 0u;  // zero all operand tiles
   __syncwarp();
-  {  // rows of ones (bf16 1.0 = 0x3F80): A2 stack row 64 (chunk 8) and, for C == 16, A1 stack row 112 (chunk 14)
+  {  // rows of ones (bf16 1.0 = 0x3F80): A2 stack row 64 (chunk 8) and A1 stack row 64 + C
     const int s = lane;
-    *reinterpret_cast<unsigned short*>(wsb + BW::A2 + 8 * LP_TC_SBO + (s >> 3) * LP_TC_LBO + (s & 7) * 16) = 0x3F80;
-    if (C == 16)
-      *reinterpret_cast<unsigned short*>(wsb + BW::A1 + 14 * LP_TC_SBO + (s >> 3) * LP_TC_LBO + (s & 7) * 16) = 0x3F80;
+    *reinterpret_cast<unsigned short*>(wsb + B::A2 + 8 * LP_TC_SBO + (s >> 3) * LP_TC_LBO + (s & 7) * 16) = 0x3F80;
+    *reinterpret_cast<unsigned short*>(wsb + B::A1 + B::ONES * LP_TC_SBO + (s >> 3) * LP_TC_LBO + (s & 7) * 16) = 0x3F80;
   }
   const unsigned base_lo = lp_tc_desc_lo(wsb);
   if (threadIdx.x == 0) {
@@ -700,7 +714,8 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
   lp_tc_fence_after();
   const unsigned tmem = *tmem_slot;
   if (threadIdx.x == 0) {  // zero the accumulators: D = 0 * 0 with accumulate off (dY tiles are zero)
-    lp_issue_dw<32>(tmem, base_lo, wsb, 0);  // <32>: clears every column range
+    lp_issue_dw<C>(tmem, base_lo, wsb, 0);
+    lp_issue_enc<C>(tmem, base_lo, wsb, 0);
     lp_tc_commit(bars + nwarps);
   }
   lp_mbar_wait(bars + nwarps, 0);
@@ -740,18 +755,16 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
       const int ray = rbase + 8 * i + g;
       gF[i] = (ray < R.n && t < D.n_feat) ? io.g_feat[(long long)ray * io.g_feat_stride + t] : 0.f;
     }
-    float genc[2][4][4];
+    float S[2][4][4];  // sum over steps of the colour-hidden gradient (-> encoding gradient, encoding product)
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int n = 0; n < 4; ++n)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) genc[mt][n][i] = 0.f;
+        for (int i = 0; i < 4; ++i) S[mt][n][i] = 0.f;
 
     for (int step = 0; step < tot; ++step) {
       if ((step & LP_ALIGN_MASK) == 0) __syncthreads();
-      // operand tiles of the previous hand-off must have been consumed by the tensor core
-      if (iter > 0) lp_mbar_wait(bars + warp, (iter - 1) & 1);
       // ------------------------------ forward recompute ------------------------------
       const Sched sc = lp_sched(step, M);
       float depth[4], delta[4];
@@ -771,14 +784,16 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
           lp_gather_lane<C, true>(G, me.b, sx, sy, sz, soob, xs, lane);
 #endif
           __syncwarp();
+          // operand tiles of the previous hand-off must have been consumed by the tensor core
+          if (iter > 0) lp_mbar_wait(bars + warp, (iter - 1) & 1);
           lp_read_rows<C>(xs, g, t, xa);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           lp_depth_delta(sc, rnear[i], rfar[i], depth[i], delta[i]);
 #pragma unroll
-          for (int k = 0; k < C / 16; ++k) {  // x0 block of A1: stack rows 96 + 16k + 4t .. +3, sample-group i
-            unsigned char* p8 = wsb + BW::A1 + (12 + 2 * k + (t >> 1)) * LP_TC_SBO + i * LP_TC_LBO + g * 16 + 8 * (t & 1);
+          for (int k = 0; k < C / 16; ++k) {  // x0 block of A1: stack rows 64 + 16k + 4t .. +3, sample-group i
+            unsigned char* p8 = wsb + B::A1 + (8 + 2 * k + (t >> 1)) * LP_TC_SBO + i * LP_TC_LBO + g * 16 + 8 * (t & 1);
             *reinterpret_cast<uint2*>(p8) = make_uint2(lp_pack_bf16x2(xa[i][4 * k], xa[i][4 * k + 1]),
                                                        lp_pack_bf16x2(xa[i][4 * k + 2], xa[i][4 * k + 3]));
           }
@@ -792,19 +807,19 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
         }
         lp_relu_to_a(acc, a);
         m_h1 = lp_mask_a(a);
-        lp_tile_put_a(wsb + BW::A1, 0, a, g, t);
+        lp_tile_put_a(wsb + B::A1, 0, a, g, t);
         lp_init_bias(acc, bias + 32, t);
         lp_layer3x<4>(smem + L::F_T1, acc, a, lane);
         lp_relu_to_a(acc, tr);
         m_tr = lp_mask_a(tr);
-        lp_tile_put_a(wsb + BW::A1, 4, tr, g, t);
+        lp_tile_put_a(wsb + B::A1, 4, tr, g, t);
         lp_init_bias(acc, bias + 64, t);
         lp_layer3x<4>(smem + L::F_O0, acc, tr, lane);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) { last[mt][0] = last[mt][2] = bias[128 + 2 * t]; last[mt][1] = last[mt][3] = bias[128 + 2 * t + 1]; }
         lp_relu_to_a(acc, a);
         m_ho = lp_mask_a(a);
-        lp_tile_put_a(wsb + BW::A2, 4, a, g, t);
+        lp_tile_put_a(wsb + B::A2, 4, a, g, t);
         lp_layer3x_n1(smem + L::F_LO, last, a, lane);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
@@ -819,12 +834,11 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
 #endif
             tr[mt][n][0] += e0.x; tr[mt][n][2] += e0.y; tr[mt][n][1] += e1.x; tr[mt][n][3] += e1.y;
           }
-        lp_tile_put_a(wsb + BW::A1, 8, tr, g, t);
         lp_init_bias(acc, bias + 96, t);
         lp_layer3x<4>(smem + L::F_C0, acc, tr, lane);
         lp_relu_to_a(acc, a);
         m_hc = lp_mask_a(a);
-        lp_tile_put_a(wsb + BW::A2, 0, a, g, t);
+        lp_tile_put_a(wsb + B::A2, 0, a, g, t);
         lp_layer3x_n1(smem + L::F_LC, last, a, lane);
       }
       // ------------------------------ compositing gradient ------------------------------
@@ -854,7 +868,7 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
       {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {  // last-layer gradient tile: columns 2t, 2t+1 (chunk 0)
-          unsigned char* p = wsb + BW::DYL + (2 * mt) * LP_TC_LBO + g * 16 + 4 * t;
+          unsigned char* p = wsb + B::DYL + (2 * mt) * LP_TC_LBO + g * 16 + 4 * t;
           *reinterpret_cast<unsigned*>(p) = lp_pack_bf16x2(dl[mt][0], dl[mt][1]);
           *reinterpret_cast<unsigned*>(p + LP_TC_LBO) = lp_pack_bf16x2(dl[mt][2], dl[mt][3]);
         }
@@ -875,8 +889,14 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
       }
       lp_gate_c(d1, m_hc);
       lp_gate_c(d2, m_ho);
-      lp_tile_put_c(wsb + BW::DY + 2 * 2048, d1, g, t);  // dY of the colour hidden layer
-      lp_tile_put_c(wsb + BW::DY + 1 * 2048, d2, g, t);  // dY of the opacity hidden layer
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) S[mt][n][i] += d1[mt][n][i];
+      lp_tile_put_c(wsb + B::DY + 2 * 2048, d1, g, t);  // dY of the colour hidden layer
+      lp_tile_put_c(wsb + B::DY + 1 * 2048, d2, g, t);  // dY of the opacity hidden layer
       lp_c_to_a_tf32(d1, a);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -885,16 +905,10 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
 #pragma unroll
           for (int i = 0; i < 4; ++i) d1[mt][n][i] = 0.f;
       lp_dx<4, 4>(smem + L::X_C0, d1, a, lane);  // d_xc (C-fragment order)
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int n = 0; n < 4; ++n)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) genc[mt][n][i] += d1[mt][n][i];
       lp_c_to_a_tf32(d2, a);
       lp_dx<4, 4>(smem + L::X_O0, d1, a, lane);  // d1 = d_t = d_xc + d_ho' Wo0^T
       lp_gate_c(d1, m_tr);
-      lp_tile_put_c(wsb + BW::DY + 0 * 2048, d1, g, t);  // dY of trunk layer 1
+      lp_tile_put_c(wsb + B::DY + 0 * 2048, d1, g, t);  // dY of trunk layer 1
       lp_c_to_a_tf32(d1, a);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -904,7 +918,7 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
           for (int i = 0; i < 4; ++i) d2[mt][n][i] = 0.f;
       lp_dx<4, 4>(smem + L::X_T1, d2, a, lane);  // d_h1
       lp_gate_c(d2, m_h1);
-      lp_tile_put_c(wsb + BW::DY + 3 * 2048, d2, g, t);  // dY of trunk layer 0
+      lp_tile_put_c(wsb + B::DY + 3 * 2048, d2, g, t);  // dY of trunk layer 0
       // hand the operand tiles to the tensor core
       lp_fence_async_smem();
       __syncwarp();
@@ -940,17 +954,49 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
       if (me.active) lp_splat_lane<C>(G, io.g_grid, me.b, sx, sy, sz, soob, xs, lane);
 #endif
     }
-    // ray-encoding gradient of this tile
+    // ---- per-tile tail: the ray encoding enters the colour branch as a per-ray constant, so both its
+    // gradient (S Wc0^T) and its share of dWc0 (enc^T S) need only the step-sum S ----
+    if (iter > 0) lp_mbar_wait(bars + warp, (iter - 1) & 1);
+    {
+      const int q = min(rbase + lane, R.n - 1);
+      const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)q * H);
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const int r0 = rbase + 16 * mt + g, r1 = r0 + 8;
-        if (r0 < R.n)
-          *reinterpret_cast<float2*>(io.g_enc + (long long)r0 * H + 8 * n + 2 * t) = make_float2(genc[mt][n][0], genc[mt][n][1]);
-        if (r1 < R.n)
-          *reinterpret_cast<float2*>(io.g_enc + (long long)r1 * H + 8 * n + 2 * t) = make_float2(genc[mt][n][2], genc[mt][n][3]);
+      for (int c = 0; c < 4; ++c) {  // features 8c..8c+7 of sample `lane` = 16 contiguous bytes of chunk c
+        const float4 u = __ldg(e4 + 2 * c), v = __ldg(e4 + 2 * c + 1);
+        *reinterpret_cast<uint4*>(wsb + B::A1 + c * LP_TC_SBO + (lane >> 3) * LP_TC_LBO + (lane & 7) * 16) =
+            make_uint4(lp_pack_bf16x2(u.x, u.y), lp_pack_bf16x2(u.z, u.w), lp_pack_bf16x2(v.x, v.y), lp_pack_bf16x2(v.z, v.w));
       }
+    }
+    lp_tile_put_c(wsb + B::DY + 2 * 2048, S, g, t);
+    lp_fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      lp_tc_fence_after();
+      lp_issue_enc<C>(tmem, base_lo, wsb, 1);
+      lp_tc_commit(bars + warp);
+    }
+    ++iter;
+    {
+      float a[2][4][4], genc[2][4][4];
+      lp_c_to_a_tf32(S, a);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) genc[mt][n][i] = 0.f;
+      lp_dx<4, 4>(smem + L::X_C0, genc, a, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const int r0 = rbase + 16 * mt + g, r1 = r0 + 8;
+          if (r0 < R.n)
+            *reinterpret_cast<float2*>(io.g_enc + (long long)r0 * H + 8 * n + 2 * t) = make_float2(genc[mt][n][0], genc[mt][n][1]);
+          if (r1 < R.n)
+            *reinterpret_cast<float2*>(io.g_enc + (long long)r1 * H + 8 * n + 2 * t) = make_float2(genc[mt][n][2], genc[mt][n][3]);
+        }
+    }
   }
   // ---- drain: every warp waits for its last hand-off, then the CTA reads the accumulators ----
   if (iter > 0) lp_mbar_wait(bars + warp, (iter - 1) & 1);
@@ -961,35 +1007,43 @@ __global__ void __launch_bounds__(256) lp_render_bwd_fast_kernel(LpRays R, LpMar
     const LpLayer &t0 = D.trunk.l[0], &t1 = D.trunk.l[1], &o0 = D.opacity.l[0], &o1 = D.opacity.l[1],
                   &c0 = D.color.l[0], &c1 = D.color.l[1];
     float v[32];
-    if (warp < 4) {  // diagonal blocks of A1 x B_j: warp w owns TMEM lanes 32w.. = stack rows 32w..
-      lp_tmem_ld32(tmem, 32 * warp, TM_W + 32 * warp, v);
-      const LpLayer& Ly = warp == 0 ? t1 : (warp == 1 ? o0 : (warp == 2 ? c0 : t0));
-      if (warp < 3 || lane < C) {
+    auto add_rows = [&](const LpLayer& Ly, int col) {  // this lane's stack row of a 32-column product
+      lp_tmem_ld32(tmem, 32 * warp, col, v);
 #pragma unroll
-        for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Ly.w_off + lane * Ly.N + n, v[n]);
+      for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Ly.w_off + lane * Ly.N + n, v[n]);
+    };
+    if (warp == 0) {         // stack rows 0..31: h1 (x d_t), and the encoding product
+      add_rows(t1, TM_W + 0);
+      add_rows(c0, TM_E);
+    } else if (warp == 1) {  // rows 32..63: trunk output (x d_ho, x d_hc)
+      add_rows(o0, TM_W + 32);
+      add_rows(c0, TM_W + 64);
+    } else if (warp == 2) {  // rows 64..64+C: grid features (x d_h1)
+      lp_tmem_ld32(tmem, 64, TM_W + 96, v);
+      if (lane < C)
+        for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + t0.w_off + lane * t0.N + n, v[n]);
+    }
+    // bias gradients of the four 32-wide layers = the row of ones (stack row 64 + C) times dY_j
+    constexpr int ones_warp = (64 + C) / 32, ones_lane = (64 + C) % 32;
+    if (warp == ones_warp) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        lp_tmem_ld32(tmem, 32 * ones_warp, TM_W + 32 * j, v);
+        const LpLayer& Lb = j == 0 ? t1 : (j == 1 ? o0 : (j == 2 ? c0 : t0));
+        if (lane == ones_lane)
+          for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Lb.b_off + n, v[n]);
       }
-      // last layer (A2 x B_last): rows 0..31 = colour hidden, 32..63 = opacity hidden, 64 = ones
-      if (warp < 3) lp_tmem_ld32(tmem, 32 * warp, TM_L, v);
+    }
+    // last layer (A2 x dY_last): rows 0..31 = colour hidden, 32..63 = opacity hidden, 64 = ones
+    if (warp < 3) {
+      lp_tmem_ld32(tmem, 32 * warp, TM_L, v);
       if (warp == 0) {
         for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.w_off + lane * c1.N + c, v[2 * c]);
       } else if (warp == 1) {
         lp_red_add1(io.g_params + o1.w_off + lane, v[1]);
-      } else if (warp == 2) {  // lane 0 <-> stack row 64 of A2: last-layer bias gradients
-        if (lane == 0) {
-          for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.b_off + c, v[2 * c]);
-          lp_red_add1(io.g_params + o1.b_off, v[1]);
-        }
-      }
-      // bias gradients of the four 32-wide layers = the row of ones times B_j
-      const int ones_warp = (C == 16) ? 3 : 2, ones_lane = (C == 16) ? 16 : 0;
-      if (warp == ones_warp) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          lp_tmem_ld32(tmem, 32 * ones_warp, ((C == 16) ? TM_W : TM_B) + 32 * j, v);
-          const LpLayer& Lb = j == 0 ? t1 : (j == 1 ? o0 : (j == 2 ? c0 : t0));
-          if (lane == ones_lane)
-            for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Lb.b_off + n, v[n]);
-        }
+      } else if (lane == 0) {
+        for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.b_off + c, v[2 * c]);
+        lp_red_add1(io.g_params + o1.b_off, v[1]);
       }
     }
   }
@@ -1054,7 +1108,7 @@ static inline bool lp_fast_render_backward_supported(const LpRenderArgs& a) { re
 template <int C>
 static int lp_fast_render_backward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
   // shared memory: weight image + (barriers, TMEM slot) + 22.4 KB of operand tiles per warp
-  const int warps = (C == 16) ? 7 : 6;
+  const int warps = (C == 16) ? 8 : 7;
   const size_t bytes = 4ull * (lpf::Lay<C>::END + 32) + (size_t)warps * lpf::BWEnd<C>::value;
   if (LP_FAST_SET_SMEM(lpf::lp_render_bwd_fast_kernel<C>, bytes)) return LP_ERR_CUDA;
   const int tiles = (a.R.n + 31) / 32;

@@ -37,6 +37,8 @@ struct dim3 {
 struct float2 { float x, y; };
 struct uint2 { unsigned x, y; };
 static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
 struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
