@@ -26,6 +26,9 @@ constexpr int H = 32;
 #ifndef LP_GATHER_STREAM
 #define LP_GATHER_STREAM 0  // backward gathers bypass L1 allocation (keeps the ray encodings L1-resident)
 #endif
+#ifndef LP_GATHER_SKIP
+#define LP_GATHER_SKIP 1  // skip the loads of a grid the sample misses entirely (mostly warp-uniform for camera rays)
+#endif
 #ifndef LP_ALIGN_MASK
 #define LP_ALIGN_MASK 0  // re-align the warps of a CTA every (mask+1) steps (I-cache sharing vs barrier stalls)
 #endif
@@ -348,6 +351,13 @@ LP_DEVICE void lp_gather_lane(const LpGridSet& G, int b, float x, float y, float
     int off[8];
     float w[8];
     const int nt = lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
+#if LP_GATHER_SKIP
+    float wsum = 0.f;
+#pragma unroll
+    for (int tp = 0; tp < 8; ++tp)
+      if (tp < nt) wsum += w[tp];
+    if (wsum == 0.f) continue;  // the sample misses this grid entirely
+#endif
 #pragma unroll
     for (int tp = 0; tp < 8; ++tp) {
       if (tp < nt) {  // zero-weight taps carry clamped (valid) addresses: load unconditionally, no branches
@@ -376,7 +386,13 @@ LP_DEVICE void lp_read_rows(const float* xs, int g, int t, float (&xa)[4][C / 4]
       xa[i][4 * k] = v.x; xa[i][4 * k + 1] = v.y; xa[i][4 * k + 2] = v.z; xa[i][4 * k + 3] = v.w;
     }
 }
-// adjoint: the ray-owner lane scatters its row of the tile into the grid gradient
+// adjoint: the ray-owner lane scatters its row of the tile into the grid gradient.  Most samples of a
+// camera ray miss a given plane (or the volume) entirely, so the products and the reductions of a
+// grid are skipped when none of its taps carries weight.
+// (A warp-level pre-aggregation of the 32 rays' overlapping footprints on the tensor core -- one
+// reduction per touched texel instead of one per ray and tap -- was built and measured: 8x fewer L2
+// reductions but ~450 extra instructions per step, and the kernel is issue-bound, not L2-atomic
+// bound: 169.6 ms vs 164.5 ms per step.  See DESIGN.md section 5.)
 template <int C>
 LP_DEVICE void lp_splat_lane(const LpGridSet& G, float* grad, int b, float x, float y, float z, float oob,
                              const float* xs, int lane) {
@@ -391,6 +407,11 @@ LP_DEVICE void lp_splat_lane(const LpGridSet& G, float* grad, int b, float x, fl
     int off[8];
     float w[8];
     const int nt = lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
+    float wsum = 0.f;  // weights are >= 0
+#pragma unroll
+    for (int tp = 0; tp < 8; ++tp)
+      if (tp < nt) wsum += w[tp];
+    if (wsum == 0.f) continue;
 #pragma unroll
     for (int tp = 0; tp < 8; ++tp) {
       if (tp < nt) {

@@ -110,3 +110,36 @@ def oracle_splat_case(c, dtype=torch.float64):
     if "mlp_params" in c:
         res.update(g_mlp=grads[1], g_input_grid=grads[2])
     return {k: v.detach() for k, v in res.items()}
+
+
+def coherent_case(c, n=64, pixel=0.02, seed=5, batch_blocks=True, mask_oob=None, plane=None):
+    """A copy of golden case `c` whose rays are replaced by `n` neighbouring pixels of a pinhole camera
+    (the layout real renders have, and the one the backward kernel's warp-level scatter aggregation is
+    built for); expected values then come from the oracle.  `plane`: optionally resize every grid to
+    plane x plane texels with fresh random contents."""
+    g = torch.Generator().manual_seed(seed)
+    c = dict(c)
+    w = int(n ** 0.5)
+    ii = torch.arange(n)
+    px, py = (ii % w).float() - w / 2, (ii // w).float() - w / 2
+    d = torch.stack([px * pixel + 0.03, py * pixel - 0.02, torch.ones(n)], -1)
+    c["directions"] = d / d.norm(dim=-1, keepdim=True)
+    c["origins"] = torch.tensor([0.1, -0.15, -2.2]).expand(n, 3).contiguous()
+    c["near"] = torch.full((n,), 1.0)
+    c["far"] = torch.full((n,), 3.4)
+    B = int(c["grid_sizes"][0][0])
+    c["grid_idx"] = ((ii * B) // n).int() if batch_blocks else torch.randint(0, B, (n,), generator=g).int()
+    c["encoding"] = torch.randn(n, c["encoding"].shape[1], generator=g)
+    c["cot_ray_length"] = torch.randn(n, generator=g)
+    c["cot_nlt"] = torch.randn(n, generator=g)
+    c["cot_features"] = torch.randn(n, c["cot_features"].shape[1], generator=g)
+    if mask_oob is not None:
+        cfg = c["cfg"].copy()
+        cfg[2] = int(mask_oob)
+        c["cfg"] = cfg
+    if plane is not None:
+        sizes = np.array([[int(v) if int(v) == 1 or j in (0, 4) else plane for j, v in enumerate(s)] for s in c["grid_sizes"]])
+        c["grid_sizes"] = sizes
+        rows = int(sum(int(np.prod(s[:4])) for s in sizes))
+        c["grid"] = torch.randn(rows, int(sizes[0][4]), generator=g)
+    return c

@@ -6,7 +6,7 @@ to 2e-4 (mean|d|/mean|ref|)."""
 import pytest
 import torch
 
-from _golden import (case_names, load_case, oracle_render_case, oracle_splat_case, rel_err,
+from _golden import (case_names, coherent_case, load_case, oracle_render_case, oracle_splat_case, rel_err,
                      renderer_cfg, splat_cfg)
 from _lowlevel import render_case, splat_case
 
@@ -42,6 +42,23 @@ def test_renderer_cabi_vs_golden(lib, name):
         assert rel_err(v, c["naive_" + k]) < tol, (name, k, "naive", rel_err(v, c["naive_" + k]))
         if not noisy_pad and not has_inf:  # see tests/test_oracle_golden.py for the exclusions
             assert rel_err(v, c["triton_" + k]) < tol, (name, k, "triton")
+
+
+@pytest.mark.parametrize("name,n,pixel,plane,mask", [
+    ("render_triplane_inf_gain", 1024, 0.002, 64, 0),   # heavily overlapping footprints
+    ("render_triplane_inf_gain", 1024, 0.004, 64, 1),   # + out-of-bounds masking
+    ("render_triplane_inf_gain", 400, 0.05, 64, 0),     # wide footprints
+    ("render_c32_b1", 576, 0.003, 48, 1),               # 32 channels
+])
+def test_renderer_coherent_rays_vs_oracle(lib, name, n, pixel, plane, mask):
+    """Camera-like neighbouring rays (what a render looks like, unlike the golden cases' random rays):
+    overlapping footprints contend on the same texels and many samples miss the planes."""
+    c = coherent_case(load_case(name), n=n, pixel=pixel, mask_oob=mask, plane=plane)
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cuda")
+    for k, v in got.items():
+        tol = TOL_GMLP_TINY if k == "g_mlp" else (TOL_GRAD if k.startswith("g_") else TOL)
+        assert rel_err(v, want[k]) < tol, (name, k, rel_err(v, want[k]))
 
 
 @pytest.mark.parametrize("name", case_names("splat_"))

@@ -7,7 +7,7 @@ import subprocess
 import pytest
 import torch
 
-from _golden import case_names, load_case, rel_err
+from _golden import case_names, coherent_case, load_case, oracle_render_case, rel_err
 from _lowlevel import render_case, splat_case
 from lightplane_b200 import _cabi
 
@@ -42,3 +42,16 @@ def test_hostsim_splatter(lib, name):
     for k, v in got.items():
         assert torch.isfinite(v).all(), (name, k)
         assert rel_err(v, c["naive_" + k]) < 2e-4, (name, k, rel_err(v, c["naive_" + k]))
+
+
+@pytest.mark.parametrize("name,pixel,mask", [("render_triplane_inf_gain", 0.02, 0), ("render_triplane_inf_gain", 0.08, 1),
+                                             ("render_c32_b1", 0.03, 1)])
+def test_hostsim_renderer_coherent_rays(lib, name, pixel, mask):
+    """Neighbouring-pixel rays (overlapping footprints, many samples outside the planes), unlike the
+    golden cases' random rays."""
+    c = coherent_case(load_case(name), n=64, pixel=pixel, mask_oob=mask)
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cpu")
+    for k, v in got.items():
+        tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
+        assert rel_err(v, want[k]) < tol, (name, k, rel_err(v, want[k]))
