@@ -8,6 +8,11 @@
 #include "lp_render_generic.cuh"
 #include "lp_splat.cuh"
 #include "lp_render_fast.cuh"
+#include "lp_render_tc.cuh"
+
+#ifndef LP_USE_TC_FWD
+#define LP_USE_TC_FWD 1  // forward fast path: 1 = tcgen05 thread-per-sample kernel, 0 = mma.sync kernel
+#endif
 
 static thread_local char g_err[512] = "";
 
@@ -227,8 +232,11 @@ int lp_render_forward(void* stream, const lp_march_cfg* cfg, const lp_decoder_sp
   if (features_stride < a.D.n_feat) LP_FAIL(LP_ERR_INVALID_ARG, "features_stride < num_color_used");
   cudaStream_t st = (cudaStream_t)stream;
   if (lp_fast_render_supported(a)) {
-    if ((rc = lp_fast_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance,
-                                     out_features, features_stride)))
+    rc = LP_USE_TC_FWD ? lptc::lp_tc_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance,
+                                                    out_features, features_stride)
+                       : lp_fast_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance,
+                                                out_features, features_stride);
+    if (rc)
       LP_FAIL(rc, "fast forward launch setup failed");
     return lp_check_launch("lp_render_forward(fast)");
   }

@@ -210,4 +210,62 @@ LP_DEVICE void lp_tmem_ld32(unsigned tmem_base, int lane_base, int col, float (&
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
+// ---- TMEM-sourced ("TS") MMAs of the thread-per-sample MLP chain (lp_render_tc.cuh): A lives in TMEM
+// (row m of A in TMEM lane m, written by tcgen05.st), B in shared memory, K-major, no swizzle:
+//   bf16:  element (n, k) at (n/8)*nstride + (k/8)*128 + (n%8)*16 + (k%8)*2, two A elements per column
+//   tf32:  element (n, k) at (n/8)*nstride + (k/4)*128 + (n%8)*16 + (k%4)*4, one A element per column
+// Descriptor field 1 (bits 16..29) is the K-direction core-matrix stride, field 2 (bits 32..45) the
+// N-direction stride (validated by tools/tc_test2.cu / tc_test3.cu).  One MMA covers K = 32 bytes.
+LP_DEVICE unsigned lp_tc_kdesc_lo(const void* smem_ptr) { return ((lp_smem_u32(smem_ptr) >> 4) & 0x3FFF) | (8u << 16); }
+typedef unsigned lp_kdesc_t;
+LP_DEVICE lp_kdesc_t lp_tc_kadv(lp_kdesc_t lo, int bytes) { return lo + (unsigned)(bytes >> 4); }
+LP_DEVICE void lp_tc_mma_ts(bool tf32, unsigned d_taddr, unsigned a_taddr, unsigned b_lo, int nstride, int n, int accumulate) {
+  const unsigned fmt = tf32 ? 2u : 1u;
+  const unsigned idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(n >> 3) << 17) | (8u << 24);
+  const unsigned hi = (unsigned)(nstride >> 4) | (1u << 14);
+  if (tf32)
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d_taddr), "r"(a_taddr), "r"(b_lo),
+                 "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d_taddr), "r"(a_taddr), "r"(b_lo),
+                 "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// warp-collective: lane i writes NW consecutive columns of TMEM lane 32*(warp%4)+i
+template <int NW>
+LP_DEVICE void lp_tmem_st(unsigned taddr, const unsigned (&v)[NW]) {
+  static_assert(NW == 8 || NW == 16, "8 or 16 columns");
+  if (NW == 8)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::"r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(taddr) : "memory");
+  else
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
+                 ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                 "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(taddr) : "memory");
+}
+LP_DEVICE void lp_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// this thread's TMEM address for column `col`: lanes 32*(warp%4).. of the CTA's allocation
+LP_DEVICE unsigned lp_taddr(unsigned tmem_base, int warp_in_group, int col) {
+  return tmem_base + ((unsigned)(warp_in_group * 32) << 16) + (unsigned)col;
+}
+LP_DEVICE void lp_tmem_ld32u(unsigned taddr, float (&v)[32]) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+// named barrier over `nthreads` threads (ids 1..15; 0 is __syncthreads)
+LP_DEVICE void lp_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 #endif  // !LP_HOSTSIM
+

@@ -67,6 +67,8 @@ struct BlockCtx {
   unsigned char* smem;
   std::vector<WarpCtx>* warps;
   float* tmem;  // emulated tensor memory: [128 lanes][512 columns]
+  std::mutex named_mu;
+  std::unique_ptr<std::barrier<>> named[16];
 };
 
 struct ThreadCtx {
@@ -98,7 +100,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
         unsigned char* smem_aligned =
             reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem.data()) + 63) & ~uintptr_t(63));
         std::vector<float> tmem(128 * 512, 0.f);
-        BlockCtx bctx{&block_bar, smem_aligned, &warps, tmem.data()};
+        BlockCtx bctx;
+        bctx.bar = &block_bar; bctx.smem = smem_aligned; bctx.warps = &warps; bctx.tmem = tmem.data();
         std::vector<std::thread> threads;
         threads.reserve(nthreads);
         for (unsigned t = 0; t < nthreads; ++t) {
@@ -282,4 +285,78 @@ static inline void lp_tc_mma_bf16_off(unsigned tmem_base, int col, unsigned, con
                                       int accumulate) {
   const unsigned char* b = static_cast<const unsigned char*>(base);
   lp_tc_mma_bf16(tmem_base, col, b + a_off, b + b_off, n, accumulate);
+}
+
+// ---- TS MMAs / tcgen05.st / named barriers (see lp_platform.cuh); TMEM words hold raw 32-bit patterns ----
+static inline unsigned lp_hs_tmem_word(int lane, int col) {
+  unsigned u; std::memcpy(&u, &lp_hostsim::g_ctx->block->tmem[lane * 512 + col], 4); return u;
+}
+struct LpHsKDesc { const unsigned char* p; };
+static inline const unsigned char* lp_tc_kdesc_lo(const void* smem_ptr) { return static_cast<const unsigned char*>(smem_ptr); }
+typedef const unsigned char* lp_kdesc_t;
+static inline lp_kdesc_t lp_tc_kadv(lp_kdesc_t p, int bytes) { return p + bytes; }
+static inline void lp_tc_mma_ts(bool tf32, unsigned d_taddr, unsigned a_taddr, const unsigned char* b, int nstride, int n,
+                                int accumulate) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  float* T = lp_hostsim::g_ctx->block->tmem;
+  const int dcol = d_taddr & 0xffff, acol = a_taddr & 0xffff;
+  const int K = tf32 ? 8 : 16;
+  for (int m = 0; m < 128; ++m) {
+    float a[16];
+    for (int k = 0; k < K; ++k) {
+      if (tf32) {
+        a[k] = lp_hs_trunc_tf32(T[m * 512 + acol + k]);
+      } else {
+        const unsigned w = lp_hs_tmem_word(m, acol + k / 2);
+        const unsigned u = (k & 1) ? (w & 0xffff0000u) : (w << 16);
+        std::memcpy(&a[k], &u, 4);
+      }
+    }
+    for (int j = 0; j < n; ++j) {
+      float acc = accumulate ? T[m * 512 + dcol + j] : 0.f;
+      for (int k = 0; k < K; ++k) {
+        float bv;
+        if (tf32) {
+          std::memcpy(&bv, b + (j / 8) * nstride + (k / 4) * 128 + (j % 8) * 16 + (k % 4) * 4, 4);
+          bv = lp_hs_trunc_tf32(bv);
+        } else {
+          bv = lp_hs_bf16(b, (j / 8) * nstride + (k / 8) * 128 + (j % 8) * 16 + (k % 8) * 2);
+        }
+        acc += a[k] * bv;
+      }
+      T[m * 512 + dcol + j] = acc;
+    }
+  }
+}
+static inline unsigned lp_taddr(unsigned tmem_base, int warp_in_group, int col) {
+  return tmem_base + ((unsigned)(warp_in_group * 32) << 16) + (unsigned)col;
+}
+template <int NW>
+static inline void lp_tmem_st(unsigned taddr, const unsigned (&v)[NW]) {
+  float* T = lp_hostsim::g_ctx->block->tmem;
+  const int row = (int)(taddr >> 16) + lp_hostsim::g_ctx->lane, col = taddr & 0xffff;
+  for (int j = 0; j < NW; ++j) std::memcpy(&T[row * 512 + col + j], &v[j], 4);
+}
+static inline void lp_tmem_wait_st() {}
+static inline void lp_tmem_ld32u(unsigned taddr, float (&v)[32]) {
+  const float* T = lp_hostsim::g_ctx->block->tmem;
+  const int row = (int)(taddr >> 16) + lp_hostsim::g_ctx->lane, col = taddr & 0xffff;
+  for (int j = 0; j < 32; ++j) v[j] = T[row * 512 + col + j];
+}
+static inline void lp_bar_sync(int id, int nthreads) {
+  auto* b = lp_hostsim::g_ctx->block;
+  std::barrier<>* bar;
+  {
+    std::lock_guard<std::mutex> lk(b->named_mu);
+    if (!b->named[id]) b->named[id].reset(new std::barrier<>(nthreads));
+    bar = b->named[id].get();
+  }
+  bar->arrive_and_wait();
+}
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+  unsigned long long v = ((unsigned long long)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+  return r;
 }
