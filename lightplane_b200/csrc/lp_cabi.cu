@@ -10,6 +10,9 @@
 #include "lp_render_fast.cuh"
 #include "lp_render_tc.cuh"
 
+#ifndef LP_USE_TC_BWD
+#define LP_USE_TC_BWD 1
+#endif
 #ifndef LP_USE_TC_FWD
 #define LP_USE_TC_FWD 1  // forward fast path: 1 = tcgen05 thread-per-sample kernel, 0 = mma.sync kernel
 #endif
@@ -277,7 +280,8 @@ int lp_render_backward(void* stream, const lp_march_cfg* cfg, const lp_decoder_s
   io.g_feat_stride = grad_features_stride;
   io.g_grid = grad_grid; io.g_cgrid = grad_color_grid; io.g_params = grad_mlp_params; io.g_enc = grad_encoding;
   if (lp_fast_render_supported(a) && lp_fast_render_backward_supported(a)) {
-    if ((rc = lp_fast_render_backward(st, a, mlp_params, io))) LP_FAIL(rc, "fast backward launch setup failed");
+    rc = LP_USE_TC_BWD ? lptc::lp_tc_render_backward(st, a, mlp_params, io) : lp_fast_render_backward(st, a, mlp_params, io);
+    if (rc) LP_FAIL(rc, "fast backward launch setup failed");
     return lp_check_launch("lp_render_backward(fast)");
   }
   const int pf = (a.D.n_params + 3) & ~3;

@@ -232,6 +232,17 @@ LP_DEVICE void lp_tc_mma_ts(bool tf32, unsigned d_taddr, unsigned a_taddr, unsig
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d_taddr), "r"(a_taddr), "r"(b_lo),
                  "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// both operands in shared memory, bf16, MN-major, no swizzle, K-group stride 128 B, MN-chunk stride `sbo`:
+// element (mn, k) at (mn/8)*sbo + (k/8)*128 + (k%8)*16 + (mn%8)*2.  D(128 x n) (+)= A(128 x 16) * B(16 x n).
+LP_DEVICE lp_kdesc_t lp_tc_mndesc_lo(const void* smem_ptr) { return ((lp_smem_u32(smem_ptr) >> 4) & 0x3FFF) | (8u << 16); }
+LP_DEVICE void lp_tc_mma_ss_mn(unsigned d_taddr, lp_kdesc_t a_lo, lp_kdesc_t b_lo, int sbo, int n, int accumulate) {
+  const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(n >> 3) << 17) | (8u << 24);
+  const unsigned hi = (unsigned)(sbo >> 4) | (1u << 14);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d_taddr), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc),
+      "r"(accumulate) : "memory");
+}
 // warp-collective: lane i writes NW consecutive columns of TMEM lane 32*(warp%4)+i
 template <int NW>
 LP_DEVICE void lp_tmem_st(unsigned taddr, const unsigned (&v)[NW]) {

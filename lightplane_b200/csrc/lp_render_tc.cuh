@@ -81,14 +81,14 @@ LP_DEVICE void lp_split2(float x0, float x1, unsigned& hi, unsigned& lo) {
   hi = __byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632);
   lo = lp_pack_bf16x2(x0 - __uint_as_float(__float_as_uint(x0) & 0xffff0000u), x1 - __uint_as_float(__float_as_uint(x1) & 0xffff0000u));
 }
-// split a row of N values and store it as this thread's row of the A operand (hi at a_col, lo at a_col + 16)
-template <int N>
+// split a row of N values and store it as this thread's row of the A operand (hi at a_col, lo at a_col + LO)
+template <int N, int LO = 16>
 LP_DEVICE void lp_stage_row(unsigned taddr_a, const float (&x)[N]) {
   unsigned hi[N / 2], lo[N / 2];
 #pragma unroll
   for (int j = 0; j < N / 2; ++j) lp_split2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
   lp_tmem_st<N / 2>(taddr_a, hi);
-  lp_tmem_st<N / 2>(taddr_a + 16, lo);
+  lp_tmem_st<N / 2>(taddr_a + LO, lo);
 }
 
 // per-group tensor-memory columns (forward): A hi 0..15 / lo 16..31, encoding hi 32..47 / lo 48..63, D 64..127
@@ -96,13 +96,13 @@ constexpr int TC_A = 0, TC_E = 32, TC_D = 64, TC_GROUP_COLS = 128;
 
 // leader thread: D(n columns) = A(K) x W, three bf16 products per 16-wide k-step
 LP_DEVICE void lp_issue_layer(unsigned tbase, int d_col, int a_col, lp_kdesc_t whi, lp_kdesc_t wlo, int ksteps, int k0,
-                              int nstride, int n, bool first) {
+                              int nstride, int n, bool first, int lo_off = 16) {
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
     if (ks < ksteps) {
       const lp_kdesc_t bh = lp_tc_kadv(whi, (k0 + ks) * 256), bl = lp_tc_kadv(wlo, (k0 + ks) * 256);
       lp_tc_mma_ts(false, tbase + d_col, tbase + a_col + 8 * ks, bh, nstride, n, !(first && ks == 0));
-      lp_tc_mma_ts(false, tbase + d_col, tbase + a_col + 16 + 8 * ks, bh, nstride, n, 1);
+      lp_tc_mma_ts(false, tbase + d_col, tbase + a_col + lo_off + 8 * ks, bh, nstride, n, 1);
       lp_tc_mma_ts(false, tbase + d_col, tbase + a_col + 8 * ks, bl, nstride, n, 1);
     }
   }
@@ -295,6 +295,420 @@ static inline int lp_tc_render_forward(cudaStream_t st, const LpRenderArgs& a, c
                                        float* out_nlt, float* out_feat, int feat_stride) {
   if (a.D.C == 16) return lp_tc_render_forward_t<16>(st, a, params, out_len, out_nlt, out_feat, feat_stride);
   return lp_tc_render_forward_t<32>(st, a, params, out_len, out_nlt, out_feat, feat_stride);
+}
+
+
+// ===========================================================================================
+// backward
+// ===========================================================================================
+// Shared memory after the forward image: the transposed weights of the three input-gradient products
+// (same K-major hi/lo form), then per group the bf16 operand tiles of the parameter-gradient GEMMs
+//     dW = A^T dY  over the group's 128 samples (the MMA's K),
+// all MN-major: element (row, sample s) at (row/8)*2048 + (s/8)*128 + (s%8)*16 + (row%8)*2, so a thread
+// writes 8 features of its sample as one 16-byte store.
+//   A1 = [h1 | trunk out | x0 | ones]   (rows 0-31, 32-63, 64..64+C, 64+C)       x  DY = [d_t | d_ho | d_hc | d_h1] (N = 128)
+//   A2 = [opacity hidden | colour hidden | ones]                                  x  DYL = [dlogit_0..2, g_raw, 0...] (N = 16)
+template <int C>
+struct BImg {
+  using I = Img<C>;
+  static constexpr int XT_HI = (I::FWD_END + 127) / 128 * 128;  // d_t:  [32 trunk][64: opacity hidden | colour hidden]
+  static constexpr int XT_LO = XT_HI + 4096;
+  static constexpr int XH_HI = XT_LO + 4096;                    // d_h1: [32][32]
+  static constexpr int XH_LO = XH_HI + 2048;
+  static constexpr int X0_HI = XH_LO + 2048;                    // d_x0: [C][32]
+  static constexpr int X0_LO = X0_HI + C * 64;
+  static constexpr int BARS = X0_LO + C * 64;                   // mbarriers + TMEM slot (128 B)
+  static constexpr int GROUPS = BARS + 128;
+  // per-group tiles
+  static constexpr int ONES1 = 8 + C / 8;                       // chunk of A1 whose first row is all ones
+  static constexpr int A1 = 0;
+  static constexpr int A2 = A1 + (ONES1 + 1) * 2048;
+  static constexpr int DY = A2 + 9 * 2048;
+  static constexpr int DYL = DY + 16 * 2048;
+  static constexpr int GROUP_BYTES = DYL + 2 * 2048;
+  static_assert(A2 + 16 * 2048 <= GROUP_BYTES, "operand window leaves the group's region");
+};
+// tensor-memory columns: per group A (hi 0..31, lo 32..63), encoding (hi 64..79, lo 80..95), D 96..159;
+// shared by the CTA: the parameter-gradient accumulators
+constexpr int BT_A = 0, BT_E = 64, BT_D = 96, BT_GROUP_COLS = 160;
+constexpr int BT_W = 320, BT_L = 448, BT_ENC = 464;
+
+template <int C>
+LP_DEVICE void lp_build_bimg(unsigned char* sm, const float* __restrict__ P, const LpDecoder& D) {
+  using B = BImg<C>;
+  const LpLayer &t0 = D.trunk.l[0], &t1 = D.trunk.l[1], &o0 = D.opacity.l[0], &c0 = D.color.l[0];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int e = tid; e < 32 * 64; e += nth) {  // B[n = trunk feature][k]: k < 32 opacity hidden k, else colour hidden k-32
+    const int n = e >> 6, k = e & 63;
+    lp_put_w(sm, B::XT_HI, B::XT_LO, n, k, 64, k < 32 ? P[o0.w_off + n * o0.N + k] : P[c0.w_off + n * c0.N + (k - 32)]);
+  }
+  for (int e = tid; e < 32 * 32; e += nth) lp_put_w(sm, B::XH_HI, B::XH_LO, e >> 5, e & 31, 32, P[t1.w_off + (e >> 5) * t1.N + (e & 31)]);
+  for (int e = tid; e < C * 32; e += nth) lp_put_w(sm, B::X0_HI, B::X0_LO, e >> 5, e & 31, 32, P[t0.w_off + (e >> 5) * t0.N + (e & 31)]);
+}
+
+// this thread's sample s: features 8*chunk .. 8*chunk+7 of a tile
+LP_DEVICE void lp_tile8(unsigned char* tile, int chunk, int s, float x0, float x1, float x2, float x3, float x4, float x5,
+                        float x6, float x7) {
+  *reinterpret_cast<uint4*>(tile + chunk * 2048 + (s >> 3) * 128 + (s & 7) * 16) =
+      make_uint4(lp_pack_bf16x2(x0, x1), lp_pack_bf16x2(x2, x3), lp_pack_bf16x2(x4, x5), lp_pack_bf16x2(x6, x7));
+}
+template <int N>
+LP_DEVICE void lp_tile_row(unsigned char* tile, int chunk0, int s, const float (&x)[N]) {
+#pragma unroll
+  for (int c = 0; c < N / 8; ++c)
+    lp_tile8(tile, chunk0 + c, s, x[8 * c], x[8 * c + 1], x[8 * c + 2], x[8 * c + 3], x[8 * c + 4], x[8 * c + 5], x[8 * c + 6], x[8 * c + 7]);
+}
+template <int N>
+LP_DEVICE unsigned lp_mask_pos(const float (&x)[N]) {
+  unsigned m = 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) m |= (x[j] > 0.f ? 1u : 0u) << j;
+  return m;
+}
+
+// leader: the group's parameter-gradient products over its 128 samples (8 k-steps of 16)
+template <int C>
+LP_DEVICE void lp_issue_dw(unsigned tmem, unsigned char* gs, int accumulate) {
+  using B = BImg<C>;
+  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), a2 = lp_tc_mndesc_lo(gs + B::A2), dy = lp_tc_mndesc_lo(gs + B::DY),
+                   dyl = lp_tc_mndesc_lo(gs + B::DYL);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    lp_tc_mma_ss_mn(tmem + BT_W, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 128, accumulate | (ks > 0));
+    lp_tc_mma_ss_mn(tmem + BT_L, lp_tc_kadv(a2, ks * 256), lp_tc_kadv(dyl, ks * 256), 2048, 16, accumulate | (ks > 0));
+  }
+}
+// encoding^T x (step-sum of the colour-hidden gradient): A1 chunks 0-3 hold the encodings, DY chunks 8-11 the sums
+template <int C>
+LP_DEVICE void lp_issue_encw(unsigned tmem, unsigned char* gs, int accumulate) {
+  using B = BImg<C>;
+  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), dy = lp_tc_mndesc_lo(gs + B::DY + 8 * 2048);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks)
+    lp_tc_mma_ss_mn(tmem + BT_ENC, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 32, accumulate | (ks > 0));
+}
+
+// adjoint of lp_gather_regs: the owner thread scatters its row into the grid gradient
+template <int C>
+LP_DEVICE void lp_splat_regs(const LpGridSet& G, float* grad, int b, float x, float y, float z, const float (&d)[C]) {
+  for (int gi = 0; gi < G.n; ++gi) {
+    int off[8];
+    float w[8];
+    const int nt = lpf::lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
+    float wsum = 0.f;
+#pragma unroll
+    for (int tp = 0; tp < 8; ++tp)
+      if (tp < nt) wsum += w[tp];
+    if (wsum == 0.f) continue;
+#pragma unroll
+    for (int tp = 0; tp < 8; ++tp) {
+      if (tp < nt) {
+        const bool on = w[tp] != 0.f;
+#pragma unroll
+        for (int k = 0; k < C / 4; ++k)
+          lp_red_add4_if(on, grad + off[tp] + 4 * k, w[tp] * d[4 * k], w[tp] * d[4 * k + 1], w[tp] * d[4 * k + 2],
+                         w[tp] * d[4 * k + 3]);
+      }
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
+                                                                   const float* __restrict__ params, LpBwdIo io) {
+  using I = Img<C>;
+  using B = BImg<C>;
+  LP_DYN_SMEM(unsigned char, sm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = tid / GT, ngroups = blockDim.x / GT, wig = warp & 3, s = tid % GT;  // s = sample row in the group
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + B::BARS);  // [2g] round trips, [2g+1] dW; [8] init
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 10);
+  unsigned char* gs = sm + B::GROUPS + grp * B::GROUP_BYTES;
+  lp_build_img<C>(sm, params, D);
+  lp_build_bimg<C>(sm, params, D);
+  for (int e = s; e < B::GROUP_BYTES / 16; e += GT) reinterpret_cast<uint4*>(gs)[e] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  // rows of ones (bf16 1.0): first row of A1 chunk ONES1 and of A2 chunk 8
+  *reinterpret_cast<unsigned short*>(gs + B::A1 + B::ONES1 * 2048 + (s >> 3) * 128 + (s & 7) * 16) = 0x3F80;
+  *reinterpret_cast<unsigned short*>(gs + B::A2 + 8 * 2048 + (s >> 3) * 128 + (s & 7) * 16) = 0x3F80;
+  if (tid == 0) {
+    for (int i = 0; i < 9; ++i) lp_mbar_init(bars + i, 1);
+    lp_mbar_init_fence();
+  }
+  if (tid < 32) lp_tmem_alloc512(tmem_slot);
+  lp_fence_async_smem();
+  lp_tc_fence_before();
+  __syncthreads();
+  lp_tc_fence_after();
+  const unsigned tmem = *tmem_slot;
+  if (tid == 0) {  // zero the accumulators: products of the (all-zero) gradient tiles with accumulate off
+    lp_issue_dw<C>(tmem, gs, 0);
+    lp_issue_encw<C>(tmem, gs, 0);
+    lp_tc_commit(bars + 8);
+  }
+  lp_mbar_wait(bars + 8, 0);
+  lp_tc_fence_after();
+  __syncthreads();
+
+  const unsigned tbase = tmem + (unsigned)(grp * BT_GROUP_COLS);
+  const unsigned tme = lp_taddr(tbase, wig, 0);
+  const bool leader = s == 0;
+  const float* F = reinterpret_cast<const float*>(sm + I::F32);
+  const lp_kdesc_t w_t0h = lp_tc_kdesc_lo(sm + I::T0_HI), w_t0l = lp_tc_kdesc_lo(sm + I::T0_LO),
+                   w_t1h = lp_tc_kdesc_lo(sm + I::T1_HI), w_t1l = lp_tc_kdesc_lo(sm + I::T1_LO),
+                   w_och = lp_tc_kdesc_lo(sm + I::OC_HI), w_ocl = lp_tc_kdesc_lo(sm + I::OC_LO),
+                   w_xth = lp_tc_kdesc_lo(sm + B::XT_HI), w_xtl = lp_tc_kdesc_lo(sm + B::XT_LO),
+                   w_xhh = lp_tc_kdesc_lo(sm + B::XH_HI), w_xhl = lp_tc_kdesc_lo(sm + B::XH_LO),
+                   w_x0h = lp_tc_kdesc_lo(sm + B::X0_HI), w_x0l = lp_tc_kdesc_lo(sm + B::X0_LO);
+  unsigned long long *bar = bars + 2 * grp, *bar_dw = bars + 2 * grp + 1;
+  int phase = 0, n_dw = 0;
+  const int num_tiles = (R.n + GT - 1) / GT;
+  const int tot = M.S + M.S_inf;
+
+  // hand-off of a staged A operand to the leader, who issues and commits to `bar` (ISSUE ends with that commit);
+  // everyone then waits for the result
+#define LP_TC_ROUND(ISSUE)                 \
+  lp_tmem_wait_st();                       \
+  lp_tc_fence_before();                    \
+  lp_bar_sync(1 + grp, GT);                \
+  if (leader) {                            \
+    lp_tc_fence_after();                   \
+    ISSUE;                                 \
+  }                                        \
+  lp_mbar_wait(bar, phase);                \
+  phase ^= 1;                              \
+  lp_tc_fence_after();
+
+  for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
+    const Ray1 me = lpf::lp_load_ray1(R, tile * GT + s, G.g[0].B);
+    const int q = me.active ? me.ray : R.n - 1;
+    {
+      float e[32];
+      const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)q * H);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 v = __ldg(e4 + k);
+        e[4 * k] = v.x; e[4 * k + 1] = v.y; e[4 * k + 2] = v.z; e[4 * k + 3] = v.w;
+      }
+      lp_stage_row<32, 16>(tme + BT_E, e);
+    }
+    // per-ray constants of the compositing gradient (renderer_bw.py:300-420)
+    const float g_len = me.active ? io.g_len[q] : 0.f, g_nlt = me.active ? io.g_nlt[q] : 0.f;
+    float gF[3], total = g_len * io.len[q];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      gF[c] = (me.active && c < D.n_feat) ? io.g_feat[(long long)q * io.g_feat_stride + c] : 0.f;
+      if (c < D.n_feat) total = fmaf(gF[c], io.feat[(long long)q * io.feat_stride + c], total);
+    }
+    float nlt = 0.f, T = 1.f, prefix = 0.f;
+    float S[32];  // sum over steps of the colour-hidden gradient
+#pragma unroll
+    for (int j = 0; j < 32; ++j) S[j] = 0.f;
+
+    for (int step = 0; step < tot; ++step) {
+      const Sched sc = lpf::lp_sched(step, M);
+      float depth, delta;
+      lpf::lp_depth_delta(sc, me.near, me.far, depth, delta);
+      float px = me.ox + depth * me.dx, py = me.oy + depth * me.dy, pz = me.oz + depth * me.dz;
+      if (M.contract) lp_contract(px, py, pz);
+      const float oob = M.mask_oob ? lp_in_bounds(px, py, pz) : 1.f;
+      unsigned m_h1, m_tr, m_ho, m_hc;
+      float v[32];
+      {
+        float x0[C];
+        lp_gather_regs<C>(G, me.b, px, py, pz, oob, x0);
+        // the previous step's parameter-gradient products must have consumed the tiles
+        if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
+        lp_tile_row<C>(gs + B::A1, 8, s, x0);
+        lp_stage_row<C, 32>(tme + BT_A, x0);
+      }
+      // ------------------------------ forward recompute ------------------------------
+      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, true, 32); lp_tc_commit(bar));
+      lp_tmem_ld32u(tme + BT_D, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + j], 0.f);
+      m_h1 = lp_mask_pos(v);
+      lp_tile_row<32>(gs + B::A1, 0, s, v);
+      lp_stage_row<32, 32>(tme + BT_A, v);
+      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_t1h, w_t1l, 2, 0, 512, 32, true, 32); lp_tc_commit(bar));
+      lp_tmem_ld32u(tme + BT_D, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + 32 + j], 0.f);
+      m_tr = lp_mask_pos(v);
+      lp_tile_row<32>(gs + B::A1, 4, s, v);
+      lp_stage_row<32, 32>(tme + BT_A, v);
+      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_och, w_ocl, 2, 0, 1024, 64, true, 32);
+                  lp_issue_layer(tbase, BT_D, BT_E, w_och, w_ocl, 2, 2, 1024, 64, false, 16); lp_tc_commit(bar));
+      float raw = F[I::FBL + 3], lg0 = F[I::FBL], lg1 = F[I::FBL + 1], lg2 = F[I::FBL + 2];
+      lp_tmem_ld32u(tme + BT_D, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = fmaxf(v[j] + F[I::FB + 64 + j], 0.f);
+        raw = fmaf(v[j], F[I::FWO + j], raw);
+      }
+      m_ho = lp_mask_pos(v);
+      lp_tile_row<32>(gs + B::A2, 0, s, v);
+      lp_tmem_ld32u(tme + BT_D + 32, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = fmaxf(v[j] + F[I::FB + 96 + j], 0.f);
+        const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
+        lg0 = fmaf(v[j], w.x, lg0); lg1 = fmaf(v[j], w.y, lg1); lg2 = fmaf(v[j], w.z, lg2);
+      }
+      m_hc = lp_mask_pos(v);
+      lp_tile_row<32>(gs + B::A2, 4, s, v);
+      // ------------------------------ compositing gradient ------------------------------
+      float g_raw, dl0, dl1, dl2;
+      {
+        if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
+        nlt += delta * M.gain * lp_softplus(raw);
+        const float Tn = expf(-nlt);
+        const float w = T - Tn;
+        T = Tn;
+        const float s0 = lp_sigmoid(lg0), s1 = lp_sigmoid(lg1), s2 = lp_sigmoid(lg2);
+        const float p = fmaf(depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2])));
+        prefix = fmaf(w, p, prefix);
+        const float suffix = (step == tot - 1) ? 0.f : total - prefix;
+        const float g_dop = Tn * p - suffix + g_nlt;
+        g_raw = g_dop * delta * M.gain * lp_sigmoid(raw);
+        dl0 = w * gF[0] * s0 * (1.f - s0);
+        dl1 = w * gF[1] * s1 * (1.f - s1);
+        dl2 = w * gF[2] * s2 * (1.f - s2);
+      }
+      lp_tile8(gs + B::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
+      // ------------------------------ backward sweep ------------------------------
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = ((m_ho >> j) & 1u) ? g_raw * F[I::FWO + j] : 0.f;  // d_ho
+      lp_tile_row<32>(gs + B::DY, 4, s, v);
+      lp_stage_row<32, 32>(tme + BT_A, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {                                                         // d_hc
+        const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
+        v[j] = ((m_hc >> j) & 1u) ? fmaf(dl0, w.x, fmaf(dl1, w.y, dl2 * w.z)) : 0.f;
+        S[j] += v[j];
+      }
+      lp_tile_row<32>(gs + B::DY, 8, s, v);
+      lp_stage_row<32, 32>(tme + BT_A + 16, v);
+      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_xth, w_xtl, 4, 0, 1024, 32, true, 32); lp_tc_commit(bar));
+      lp_tmem_ld32u(tme + BT_D, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = ((m_tr >> j) & 1u) ? v[j] : 0.f;                  // d_t
+      lp_tile_row<32>(gs + B::DY, 0, s, v);
+      lp_stage_row<32, 32>(tme + BT_A, v);
+      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_xhh, w_xhl, 2, 0, 512, 32, true, 32); lp_tc_commit(bar));
+      lp_tmem_ld32u(tme + BT_D, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = ((m_h1 >> j) & 1u) ? v[j] : 0.f;                  // d_h1
+      lp_tile_row<32>(gs + B::DY, 12, s, v);
+      lp_stage_row<32, 32>(tme + BT_A, v);
+      lp_fence_async_smem();  // this step's tile writes -> visible to the tensor core
+      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_x0h, w_x0l, 2, 0, 512, C, true, 32); lp_tc_commit(bar);
+                  lp_issue_dw<C>(tmem, gs, 1); lp_tc_commit(bar_dw));
+      ++n_dw;
+      {
+        float d[C];
+        lp_tmem_ld32u(tme + BT_D, v);
+#pragma unroll
+        for (int c = 0; c < C; ++c) d[c] = v[c] * oob;
+        if (me.active && oob != 0.f) lp_splat_regs<C>(G, io.g_grid, me.b, px, py, pz, d);
+      }
+    }
+    // ---- per-tile tail: encoding gradient = S Wc0^T, and the encoding's share of dWc0 = enc^T S ----
+    if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
+    {
+      float e[32];
+      const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)q * H);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 vv = __ldg(e4 + k);
+        e[4 * k] = vv.x; e[4 * k + 1] = vv.y; e[4 * k + 2] = vv.z; e[4 * k + 3] = vv.w;
+      }
+      lp_tile_row<32>(gs + B::A1, 0, s, e);
+      lp_tile_row<32>(gs + B::DY, 8, s, S);
+      lp_stage_row<32, 32>(tme + BT_A + 16, S);  // K index 32..63 of the d_t weight tile = colour hidden
+      lp_fence_async_smem();
+      float v[32];
+      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A + 16, w_xth, w_xtl, 2, 2, 1024, 32, true, 32); lp_tc_commit(bar);
+                  lp_issue_encw<C>(tmem, gs, 1); lp_tc_commit(bar_dw));
+      ++n_dw;
+      lp_tmem_ld32u(tme + BT_D, v);
+      if (me.active) {
+        float4* ge = reinterpret_cast<float4*>(io.g_enc + (long long)me.ray * H);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ge[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      }
+    }
+  }
+#undef LP_TC_ROUND
+  // ---- drain, then the CTA's first four warps read the accumulators (TMEM lane = stack row) ----
+  if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
+  lp_tc_fence_before();
+  __syncthreads();
+  lp_tc_fence_after();
+  if (warp < 4) {
+    const LpLayer &t0 = D.trunk.l[0], &t1 = D.trunk.l[1], &o0 = D.opacity.l[0], &o1 = D.opacity.l[1],
+                  &c0 = D.color.l[0], &c1 = D.color.l[1];
+    float v[32];
+    const unsigned tl = lp_taddr(tmem, warp, 0);
+    auto add_rows = [&](const LpLayer& Ly, int col) {  // this lane's stack row of a 32-column product
+      lp_tmem_ld32u(tl + col, v);
+#pragma unroll
+      for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Ly.w_off + lane * Ly.N + n, v[n]);
+    };
+    if (warp == 0) {         // stack rows 0..31: h1 (x d_t), and the encoding product
+      add_rows(t1, BT_W + 0);
+      add_rows(c0, BT_ENC);
+    } else if (warp == 1) {  // rows 32..63: trunk output (x d_ho, x d_hc)
+      add_rows(o0, BT_W + 32);
+      add_rows(c0, BT_W + 64);
+    } else if (warp == 2) {  // rows 64..64+C: grid features (x d_h1)
+      lp_tmem_ld32u(tl + BT_W + 96, v);
+      if (lane < C)
+        for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + t0.w_off + lane * t0.N + n, v[n]);
+    }
+    constexpr int ones_warp = (64 + C) / 32, ones_lane = (64 + C) % 32;  // the row of ones: bias gradients
+    if (warp == ones_warp) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        lp_tmem_ld32u(tl + BT_W + 32 * j, v);
+        const LpLayer& Lb = j == 0 ? t1 : (j == 1 ? o0 : (j == 2 ? c0 : t0));
+        if (lane == ones_lane)
+          for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Lb.b_off + n, v[n]);
+      }
+    }
+    // last layer (A2 x DYL): rows 0..31 opacity hidden, 32..63 colour hidden, 64 ones; columns dlogit_0..2, g_raw
+    if (warp < 3) {
+      lp_tmem_ld32u(tl + BT_L, v);  // 16 valid columns (the rest belongs to the next accumulator)
+      if (warp == 0) {
+        lp_red_add1(io.g_params + o1.w_off + lane * o1.N, v[3]);
+      } else if (warp == 1) {
+        for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.w_off + lane * c1.N + c, v[c]);
+      } else if (lane == 0) {
+        for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.b_off + c, v[c]);
+        lp_red_add1(io.g_params + o1.b_off, v[3]);
+      }
+    }
+  }
+  lp_tc_fence_before();
+  __syncthreads();
+  if (tid < 32) lp_tmem_dealloc512(tmem);
+}
+
+template <int C>
+static int lp_tc_render_backward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
+  const int groups = 2;
+  const size_t bytes = BImg<C>::GROUPS + (size_t)groups * BImg<C>::GROUP_BYTES;
+  if (LP_FAST_SET_SMEM(lp_render_bwd_tc_kernel<C>, bytes)) return LP_ERR_CUDA;
+  const int tiles = (a.R.n + GT - 1) / GT;
+  int blocks = (tiles + groups - 1) / groups;
+  const int max_blocks = lp_fast_num_sms();
+  if (blocks > max_blocks) blocks = max_blocks;
+  LP_LAUNCH(lp_render_bwd_tc_kernel<C>, dim3(blocks), dim3(groups * GT), bytes, st, a.R, a.M, a.D, a.G, params, io);
+  return LP_OK;
+}
+static inline int lp_tc_render_backward(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
+  if (a.D.C == 16) return lp_tc_render_backward_t<16>(st, a, params, io);
+  return lp_tc_render_backward_t<32>(st, a, params, io);
 }
 
 }  // namespace lptc

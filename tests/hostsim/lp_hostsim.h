@@ -329,6 +329,20 @@ static inline void lp_tc_mma_ts(bool tf32, unsigned d_taddr, unsigned a_taddr, c
     }
   }
 }
+static inline lp_kdesc_t lp_tc_mndesc_lo(const void* smem_ptr) { return static_cast<const unsigned char*>(smem_ptr); }
+static inline void lp_tc_mma_ss_mn(unsigned d_taddr, lp_kdesc_t a, lp_kdesc_t b, int sbo, int n, int accumulate) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  float* T = lp_hostsim::g_ctx->block->tmem;
+  const int dcol = d_taddr & 0xffff;
+  auto off = [sbo](int mn, int k) { return (mn / 8) * sbo + (k / 8) * 128 + (k % 8) * 16 + (mn % 8) * 2; };
+  for (int m = 0; m < 128; ++m)
+    for (int j = 0; j < n; ++j) {
+      float acc = accumulate ? T[m * 512 + dcol + j] : 0.f;
+      for (int k = 0; k < 16; ++k) acc += lp_hs_bf16(a, off(m, k)) * lp_hs_bf16(b, off(j, k));
+      T[m * 512 + dcol + j] = acc;
+    }
+}
 static inline unsigned lp_taddr(unsigned tmem_base, int warp_in_group, int col) {
   return tmem_base + ((unsigned)(warp_in_group * 32) << 16) + (unsigned)col;
 }
