@@ -366,6 +366,22 @@ LP_DEVICE unsigned lp_mask_pos(const float (&x)[N]) {
   return m;
 }
 
+// ReLU gate read back from the bf16 operand tile the activation was written to (this thread's own row;
+// an activation is > 0 iff its bf16 image is non-zero): x[j] survives iff feature j of the tile row != 0
+template <bool MULT_FIRST = false>
+LP_DEVICE void lp_gate_row(float (&x)[32], const unsigned char* tile, int chunk0, int s) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 w = *reinterpret_cast<const uint4*>(tile + (chunk0 + c) * 2048 + (s >> 3) * 128 + (s & 7) * 16);
+    const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (!(ww[e] & 0xffffu)) x[8 * c + 2 * e] = 0.f;
+      if (!(ww[e] >> 16)) x[8 * c + 2 * e + 1] = 0.f;
+    }
+  }
+}
+
 // leader: the group's parameter-gradient products over its 128 samples (8 k-steps of 16)
 template <int C>
 LP_DEVICE void lp_issue_dw(unsigned tmem, unsigned char* gs, int accumulate) {
@@ -465,19 +481,22 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
   const int num_tiles = (R.n + GT - 1) / GT;
   const int tot = M.S + M.S_inf;
 
-  // hand-off of a staged A operand to the leader, who issues and commits to `bar` (ISSUE ends with that commit);
-  // everyone then waits for the result
-#define LP_TC_ROUND(ISSUE)                 \
+  // A round trip to the tensor core is split in two so that independent work can run while the MMAs
+  // execute: HANDOFF publishes this thread's staged operand row and lets the leader issue (ISSUE ends
+  // with the commit to `bar`); WAIT blocks until the result is in tensor memory.
+#define LP_TC_HANDOFF(ISSUE)               \
   lp_tmem_wait_st();                       \
   lp_tc_fence_before();                    \
   lp_bar_sync(1 + grp, GT);                \
   if (leader) {                            \
     lp_tc_fence_after();                   \
     ISSUE;                                 \
-  }                                        \
+  }
+#define LP_TC_WAIT()                       \
   lp_mbar_wait(bar, phase);                \
   phase ^= 1;                              \
   lp_tc_fence_after();
+#define LP_TC_ROUND(ISSUE) LP_TC_HANDOFF(ISSUE) LP_TC_WAIT()
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
     const Ray1 me = lpf::lp_load_ray1(R, tile * GT + s, G.g[0].B);
@@ -505,36 +524,43 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
 #pragma unroll
     for (int j = 0; j < 32; ++j) S[j] = 0.f;
 
-    for (int step = 0; step < tot; ++step) {
+    // Software pipeline across steps: the gather of step n+1 is issued while the tensor core runs the
+    // first input-gradient product of step n, and the scatter of step n while it runs the first layer
+    // of step n+1 -- the two memory-bound, MMA-independent pieces hide inside the waits.
+    struct Pos { float depth, delta, x, y, z, oob; };
+    auto sample_at = [&](int step) {
+      Pos p;
       const Sched sc = lpf::lp_sched(step, M);
-      float depth, delta;
-      lpf::lp_depth_delta(sc, me.near, me.far, depth, delta);
-      float px = me.ox + depth * me.dx, py = me.oy + depth * me.dy, pz = me.oz + depth * me.dz;
-      if (M.contract) lp_contract(px, py, pz);
-      const float oob = M.mask_oob ? lp_in_bounds(px, py, pz) : 1.f;
-      unsigned m_h1, m_tr, m_ho, m_hc;
+      lpf::lp_depth_delta(sc, me.near, me.far, p.depth, p.delta);
+      p.x = me.ox + p.depth * me.dx; p.y = me.oy + p.depth * me.dy; p.z = me.oz + p.depth * me.dz;
+      if (M.contract) lp_contract(p.x, p.y, p.z);
+      p.oob = M.mask_oob ? lp_in_bounds(p.x, p.y, p.z) : 1.f;
+      return p;
+    };
+    Pos cur = sample_at(0), prev = cur;
+    float x0[C], dxp[C];  // gathered features of the current step; input gradient of the previous step
+    lp_gather_regs<C>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
+    bool have_prev = false;
+
+    for (int step = 0; step < tot; ++step) {
       float v[32];
-      {
-        float x0[C];
-        lp_gather_regs<C>(G, me.b, px, py, pz, oob, x0);
-        // the previous step's parameter-gradient products must have consumed the tiles
-        if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
-        lp_tile_row<C>(gs + B::A1, 8, s, x0);
-        lp_stage_row<C, 32>(tme + BT_A, x0);
-      }
+      // the previous step's parameter-gradient products must have consumed the tiles
+      if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
+      lp_tile_row<C>(gs + B::A1, 8, s, x0);
+      lp_stage_row<C, 32>(tme + BT_A, x0);
       // ------------------------------ forward recompute ------------------------------
-      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, true, 32); lp_tc_commit(bar));
+      LP_TC_HANDOFF(lp_issue_layer(tbase, BT_D, BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, true, 32); lp_tc_commit(bar));
+      if (have_prev && me.active && prev.oob != 0.f) lp_splat_regs<C>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp);
+      LP_TC_WAIT();
       lp_tmem_ld32u(tme + BT_D, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + j], 0.f);
-      m_h1 = lp_mask_pos(v);
       lp_tile_row<32>(gs + B::A1, 0, s, v);
       lp_stage_row<32, 32>(tme + BT_A, v);
       LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_t1h, w_t1l, 2, 0, 512, 32, true, 32); lp_tc_commit(bar));
       lp_tmem_ld32u(tme + BT_D, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + 32 + j], 0.f);
-      m_tr = lp_mask_pos(v);
       lp_tile_row<32>(gs + B::A1, 4, s, v);
       lp_stage_row<32, 32>(tme + BT_A, v);
       LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_och, w_ocl, 2, 0, 1024, 64, true, 32);
@@ -546,7 +572,6 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
         v[j] = fmaxf(v[j] + F[I::FB + 64 + j], 0.f);
         raw = fmaf(v[j], F[I::FWO + j], raw);
       }
-      m_ho = lp_mask_pos(v);
       lp_tile_row<32>(gs + B::A2, 0, s, v);
       lp_tmem_ld32u(tme + BT_D + 32, v);
 #pragma unroll
@@ -555,22 +580,21 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
         const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
         lg0 = fmaf(v[j], w.x, lg0); lg1 = fmaf(v[j], w.y, lg1); lg2 = fmaf(v[j], w.z, lg2);
       }
-      m_hc = lp_mask_pos(v);
       lp_tile_row<32>(gs + B::A2, 4, s, v);
       // ------------------------------ compositing gradient ------------------------------
       float g_raw, dl0, dl1, dl2;
       {
         if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-        nlt += delta * M.gain * lp_softplus(raw);
+        nlt += cur.delta * M.gain * lp_softplus(raw);
         const float Tn = expf(-nlt);
         const float w = T - Tn;
         T = Tn;
         const float s0 = lp_sigmoid(lg0), s1 = lp_sigmoid(lg1), s2 = lp_sigmoid(lg2);
-        const float p = fmaf(depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2])));
+        const float p = fmaf(cur.depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2])));
         prefix = fmaf(w, p, prefix);
         const float suffix = (step == tot - 1) ? 0.f : total - prefix;
         const float g_dop = Tn * p - suffix + g_nlt;
-        g_raw = g_dop * delta * M.gain * lp_sigmoid(raw);
+        g_raw = g_dop * cur.delta * M.gain * lp_sigmoid(raw);
         dl0 = w * gF[0] * s0 * (1.f - s0);
         dl1 = w * gF[1] * s1 * (1.f - s1);
         dl2 = w * gF[2] * s2 * (1.f - s2);
@@ -578,41 +602,46 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
       lp_tile8(gs + B::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
       // ------------------------------ backward sweep ------------------------------
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = ((m_ho >> j) & 1u) ? g_raw * F[I::FWO + j] : 0.f;  // d_ho
+      for (int j = 0; j < 32; ++j) v[j] = g_raw * F[I::FWO + j];  // d_ho
+      lp_gate_row(v, gs + B::A2, 0, s);
       lp_tile_row<32>(gs + B::DY, 4, s, v);
       lp_stage_row<32, 32>(tme + BT_A, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {                                                         // d_hc
         const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
-        v[j] = ((m_hc >> j) & 1u) ? fmaf(dl0, w.x, fmaf(dl1, w.y, dl2 * w.z)) : 0.f;
-        S[j] += v[j];
+        v[j] = fmaf(dl0, w.x, fmaf(dl1, w.y, dl2 * w.z));
       }
+      lp_gate_row(v, gs + B::A2, 4, s);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) S[j] += v[j];
       lp_tile_row<32>(gs + B::DY, 8, s, v);
       lp_stage_row<32, 32>(tme + BT_A + 16, v);
-      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_xth, w_xtl, 4, 0, 1024, 32, true, 32); lp_tc_commit(bar));
+      LP_TC_HANDOFF(lp_issue_layer(tbase, BT_D, BT_A, w_xth, w_xtl, 4, 0, 1024, 32, true, 32); lp_tc_commit(bar));
+      prev = cur;
+      if (step + 1 < tot) {  // prefetch the next step's features while the product runs
+        cur = sample_at(step + 1);
+        lp_gather_regs<C>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
+      }
+      LP_TC_WAIT();
       lp_tmem_ld32u(tme + BT_D, v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = ((m_tr >> j) & 1u) ? v[j] : 0.f;                  // d_t
+      lp_gate_row(v, gs + B::A1, 4, s);  // d_t
       lp_tile_row<32>(gs + B::DY, 0, s, v);
       lp_stage_row<32, 32>(tme + BT_A, v);
       LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_xhh, w_xhl, 2, 0, 512, 32, true, 32); lp_tc_commit(bar));
       lp_tmem_ld32u(tme + BT_D, v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = ((m_h1 >> j) & 1u) ? v[j] : 0.f;                  // d_h1
+      lp_gate_row(v, gs + B::A1, 0, s);  // d_h1
       lp_tile_row<32>(gs + B::DY, 12, s, v);
       lp_stage_row<32, 32>(tme + BT_A, v);
       lp_fence_async_smem();  // this step's tile writes -> visible to the tensor core
       LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_x0h, w_x0l, 2, 0, 512, C, true, 32); lp_tc_commit(bar);
                   lp_issue_dw<C>(tmem, gs, 1); lp_tc_commit(bar_dw));
       ++n_dw;
-      {
-        float d[C];
-        lp_tmem_ld32u(tme + BT_D, v);
+      lp_tmem_ld32u(tme + BT_D, v);
 #pragma unroll
-        for (int c = 0; c < C; ++c) d[c] = v[c] * oob;
-        if (me.active && oob != 0.f) lp_splat_regs<C>(G, io.g_grid, me.b, px, py, pz, d);
-      }
+      for (int c = 0; c < C; ++c) dxp[c] = v[c] * prev.oob;
+      have_prev = true;
     }
+    if (me.active && prev.oob != 0.f) lp_splat_regs<C>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp);  // last step's scatter
     // ---- per-tile tail: encoding gradient = S Wc0^T, and the encoding's share of dWc0 = enc^T S ----
     if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
     {
@@ -640,6 +669,8 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
     }
   }
 #undef LP_TC_ROUND
+#undef LP_TC_HANDOFF
+#undef LP_TC_WAIT
   // ---- drain, then the CTA's first four warps read the accumulators (TMEM lane = stack row) ----
   if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
   lp_tc_fence_before();
