@@ -7,15 +7,7 @@
 #include "lp_common.cuh"
 #include "lp_render_generic.cuh"
 #include "lp_splat.cuh"
-#include "lp_render_fast.cuh"
 #include "lp_render_tc.cuh"
-
-#ifndef LP_USE_TC_BWD
-#define LP_USE_TC_BWD 1
-#endif
-#ifndef LP_USE_TC_FWD
-#define LP_USE_TC_FWD 1  // forward fast path: 1 = tcgen05 thread-per-sample kernel, 0 = mma.sync kernel
-#endif
 
 static thread_local char g_err[512] = "";
 
@@ -234,12 +226,9 @@ int lp_render_forward(void* stream, const lp_march_cfg* cfg, const lp_decoder_sp
     LP_FAIL(LP_ERR_INVALID_ARG, "an output pointer is NULL");
   if (features_stride < a.D.n_feat) LP_FAIL(LP_ERR_INVALID_ARG, "features_stride < num_color_used");
   cudaStream_t st = (cudaStream_t)stream;
-  if (lp_fast_render_supported(a)) {
-    rc = LP_USE_TC_FWD ? lptc::lp_tc_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance,
-                                                    out_features, features_stride)
-                       : lp_fast_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance,
-                                                out_features, features_stride);
-    if (rc)
+  if (lptc::lp_tc_render_supported(a)) {
+    if ((rc = lptc::lp_tc_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance, out_features,
+                                         features_stride)))
       LP_FAIL(rc, "fast forward launch setup failed");
     return lp_check_launch("lp_render_forward(fast)");
   }
@@ -279,9 +268,8 @@ int lp_render_backward(void* stream, const lp_march_cfg* cfg, const lp_decoder_s
   io.g_len = grad_ray_length; io.g_nlt = grad_neg_log_transmittance; io.g_feat = grad_features;
   io.g_feat_stride = grad_features_stride;
   io.g_grid = grad_grid; io.g_cgrid = grad_color_grid; io.g_params = grad_mlp_params; io.g_enc = grad_encoding;
-  if (lp_fast_render_supported(a) && lp_fast_render_backward_supported(a)) {
-    rc = LP_USE_TC_BWD ? lptc::lp_tc_render_backward(st, a, mlp_params, io) : lp_fast_render_backward(st, a, mlp_params, io);
-    if (rc) LP_FAIL(rc, "fast backward launch setup failed");
+  if (lptc::lp_tc_render_supported(a)) {
+    if ((rc = lptc::lp_tc_render_backward(st, a, mlp_params, io))) LP_FAIL(rc, "fast backward launch setup failed");
     return lp_check_launch("lp_render_backward(fast)");
   }
   const int pf = (a.D.n_params + 3) & ~3;

@@ -52,18 +52,6 @@ LP_DEVICE void lp_red_add1(float* addr, float a) {
 #endif
 }
 
-// 16-byte read-only load that does not allocate in L1: the backward kernel's L1 is ~29 KB (the rest
-// of the 256 KB is shared memory) and is better spent on the per-ray encodings than on grid rows
-LP_DEVICE float4 lp_ldg4_stream(const float* p) {
-#if defined(LP_HOSTSIM)
-  return make_float4(p[0], p[1], p[2], p[3]);
-#else
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-#endif
-}
-
 LP_DEVICE float4 lp_ldg4(const float* p) {
 #if defined(LP_HOSTSIM)
   return make_float4(p[0], p[1], p[2], p[3]);
@@ -73,46 +61,11 @@ LP_DEVICE float4 lp_ldg4(const float* p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// warp-level tensor-core primitives (mma.sync m16n8k8, TF32 in / FP32 accumulate)
-// Fragment layout (lane = 4*g + t): A 16x8 row-major: a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4);
-// B 8x8: b0=(k=t,n=g) b1=(k=t+4,n=g); C 16x8: c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1).
+// Blackwell tensor-core primitives (tcgen05): accumulators and the A operand of the per-sample MLP
+// chain live in tensor memory, B operands and the parameter-gradient tiles in shared memory as
+// non-swizzled UMMA operands.  The operand forms and descriptor encodings used below are validated
+// in isolation by tools/tc_test.cu, tc_test2.cu and tc_test3.cu.
 // ---------------------------------------------------------------------------------------------
-LP_DEVICE float lp_tf32_rna(float x) {  // round-to-nearest TF32 (10-bit mantissa), as fp32 bits
-#if defined(LP_HOSTSIM)
-  unsigned u = __float_as_uint(x);
-  if ((u & 0x7f800000u) == 0x7f800000u) return x;
-  u += 0x00001000u;  // round half away from zero on the magnitude, like cvt.rna
-  u &= 0xffffe000u;
-  return __uint_as_float(u);
-#else
-  unsigned u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-#endif
-}
-
-LP_DEVICE void lp_mma_tf32(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
-#if defined(LP_HOSTSIM)
-  lp_hostsim_mma_m16n8k8(d, a, b);
-#else
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
-        "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
-#endif
-}
-
-// ---------------------------------------------------------------------------------------------
-// Blackwell async tensor-core primitives used for the parameter-gradient GEMMs of the backward
-// kernel: accumulators live in TMEM (tcgen05), operands are bf16 tiles in shared memory laid out as
-// MN-major, non-swizzled UMMA operands: element (mn, k) at byte
-//     (mn/8)*SBO + (k/8)*LBO + (k%8)*16 + (mn%8)*2,   LBO = 128, SBO = 512
-// (validated in isolation by tools/tc_test.cu).  D[128 x N] (+)= A[128 x 16] * B[16 x N].
-// ---------------------------------------------------------------------------------------------
-#define LP_TC_LBO 128
-#define LP_TC_SBO 512
-
 LP_DEVICE unsigned lp_pack_bf16x2(float lo, float hi) {  // lo -> bits 0..15, hi -> bits 16..31
 #if defined(LP_HOSTSIM)
   auto cv = [](float x) -> unsigned {
@@ -157,59 +110,10 @@ LP_DEVICE void lp_tmem_alloc512(unsigned* slot) {
 LP_DEVICE void lp_tmem_dealloc512(unsigned base) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
 }
-LP_DEVICE unsigned long long lp_tc_desc(const void* smem_ptr) {
-  unsigned long long d = 0;
-  d |= (unsigned long long)((lp_smem_u32(smem_ptr) >> 4) & 0x3FFF);
-  d |= (unsigned long long)((LP_TC_LBO >> 4) & 0x3FFF) << 16;
-  d |= (unsigned long long)((LP_TC_SBO >> 4) & 0x3FFF) << 32;
-  d |= 1ull << 46;
-  return d;
-}
-// one elected thread: D(tmem column col, 128 lanes x n cols) (+)= A(128 x 16) * B(16 x n); bf16, MN-major
-LP_DEVICE void lp_tc_mma_bf16(unsigned tmem_base, int col, const void* a, const void* b, int n, int accumulate) {
-  const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(n >> 3) << 17) | (8u << 24);
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_base + (unsigned)col),
-      "l"(lp_tc_desc(a)), "l"(lp_tc_desc(b)), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Same, with operands addressed as byte offsets from one 16-byte aligned shared-memory base whose
-// descriptor low word `base_lo` (= lp_tc_desc_lo(base)) is computed once: ~4 instructions per MMA.
-LP_DEVICE unsigned lp_tc_desc_lo(const void* smem_ptr) {
-  return ((lp_smem_u32(smem_ptr) >> 4) & 0x3FFF) | ((unsigned)(LP_TC_LBO >> 4) << 16);
-}
-LP_DEVICE void lp_tc_mma_bf16_off(unsigned tmem_base, int col, unsigned base_lo, const void*, int a_off, int b_off,
-                                   int n, int accumulate) {
-  const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(n >> 3) << 17) | (8u << 24);
-  const unsigned hi = (unsigned)(LP_TC_SBO >> 4) | (1u << 14);  // SBO at bits 32..45, version 1 at bit 46
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_base + (unsigned)col),
-      "r"(base_lo + (unsigned)(a_off >> 4)), "r"(base_lo + (unsigned)(b_off >> 4)), "r"(hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 LP_DEVICE void lp_tc_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(lp_smem_u32(bar)) : "memory");
 }
-// warp-collective: lane i receives 32 consecutive columns of TMEM lane 32*(warp%4)+i
-LP_DEVICE void lp_tmem_ld32(unsigned tmem_base, int lane_base, int col, float (&v)[32]) {
-  unsigned r[32];
-  const unsigned taddr = tmem_base + ((unsigned)lane_base << 16) + (unsigned)col;
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
-      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-}
+
 // ---- TMEM-sourced ("TS") MMAs of the thread-per-sample MLP chain (lp_render_tc.cuh): A lives in TMEM
 // (row m of A in TMEM lane m, written by tcgen05.st), B in shared memory, K-major, no swizzle:
 //   bf16:  element (n, k) at (n/8)*nstride + (k/8)*128 + (n%8)*16 + (k%8)*2, two A elements per column

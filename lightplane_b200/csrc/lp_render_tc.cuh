@@ -1,5 +1,7 @@
-// Renderer fast path, second generation: the per-sample MLP runs on the 5th-generation tensor cores
-// (tcgen05) with one THREAD per sample.
+// Renderer fast path for the default decoder shape (trunk/opacity/colour = 2/2/2 layers, hidden width
+// 32, C in {16,32} grid channels, <= 3 colour channels, no colour grid / scaffold): the per-sample MLP
+// runs on the 5th-generation tensor cores (tcgen05) with one THREAD per sample.  Other decoder shapes
+// take the generic kernels of lp_render_generic.cuh.
 //
 // A group of 128 threads marches 128 rays in lock step.  At every step each thread gathers the grid
 // features of its own sample into registers, splits them into two bf16 terms (x = hi + lo) and stores
@@ -17,12 +19,115 @@
 // of triton_src/shared/fwbw_util.py:26-150; see DESIGN.md section 4.
 #pragma once
 
-#include "lp_render_fast.cuh"
+#include "lp_render_generic.cuh"
 
 namespace lptc {
-using lpf::H;
-using lpf::Ray1;
-using lpf::Sched;
+
+constexpr int H = 32;  // hidden width of the decoder shape this path is specialised for
+
+// ---- per-ray state, depth schedule and grid taps (semantics of lp_common.cuh, 32-bit offsets) ----
+struct Ray1 {
+  float ox, oy, oz, dx, dy, dz, near, far;
+  int b, ray;
+  bool active;
+};
+LP_DEVICE Ray1 lp_load_ray1(const LpRays& R, int ray, int batch) {
+  Ray1 r;
+  r.active = ray < R.n;
+  r.ray = ray;
+  const int q = r.active ? ray : R.n - 1;
+  r.ox = R.org[3 * q]; r.oy = R.org[3 * q + 1]; r.oz = R.org[3 * q + 2];
+  r.dx = R.dir[3 * q]; r.dy = R.dir[3 * q + 1]; r.dz = R.dir[3 * q + 2];
+  r.near = R.near[q]; r.far = R.far[q];
+  r.b = min(max(R.gidx[q], 0), batch - 1);
+  return r;
+}
+
+// warp-uniform depth schedule of one step: depth = a + b*c  with per-ray (a, b) chosen by `inf`
+struct Sched {
+  float cur, prev;  // regular: j/(S-1), (j-1)/(S-1);  background: 1/n_disp(k), 1/n_disp(k-1)
+  bool inf, first_inf, single;
+};
+LP_DEVICE Sched lp_sched(int step, const LpMarch& M) {
+  Sched s;
+  s.inf = step >= M.S;
+  s.single = M.S <= 1;
+  s.first_inf = step == M.S;
+  if (!s.inf) {
+    const float inv = s.single ? 0.f : 1.f / (float)(M.S - 1);
+    s.cur = (float)step * inv;
+    s.prev = (float)(step - 1) * inv;
+  } else {
+    const int k = step - M.S;
+    auto sc = [&](int kk) {  // 1 / ((1-f) + d_inf*f), f = (kk+1)/S_inf  (see lp_depth)
+      const float f = (float)(kk + 1) / (float)M.S_inf;
+      const float omf = (float)(M.S_inf - (kk + 1)) / (float)M.S_inf;
+      return 1.f / (omf + M.disparity_at_inf * f);
+    };
+    s.cur = sc(k);
+    s.prev = sc(k - 1);
+  }
+  return s;
+}
+LP_DEVICE void lp_depth_delta(const Sched& s, float near, float far, float& depth, float& delta) {
+  if (!s.inf) {
+    if (s.single) { depth = near; delta = 1.f; return; }
+    depth = (far - near) * s.cur + near;
+    delta = depth - ((far - near) * s.prev + near);
+  } else {
+    depth = far * s.cur;
+    delta = depth - (s.first_inf ? ((far - near) * 1.f + near) : far * s.prev);
+  }
+}
+
+// taps of one grid with 32-bit element offsets (the fast path requires < 2^31 grid elements)
+LP_DEVICE void lp_axis_i(float p, int size, int& i0, float& frac) {
+  float i = ((p + 1.f) * 0.5f) * (float)size - 0.5f;
+  if (size <= 1) i = 0.f;
+  const float f0 = floorf(i);
+  frac = i - f0;
+  i0 = (int)fminf(fmaxf(f0, -2.f), (float)size);  // clamp keeps the int conversion defined
+}
+LP_DEVICE void lp_corner_i(int i0, float frac, int size, float& w0, float& w1, int& c0, int& c1) {
+  w0 = ((unsigned)i0 < (unsigned)size) ? 1.f - frac : 0.f;
+  w1 = ((unsigned)(i0 + 1) < (unsigned)size) ? frac : 0.f;
+  c0 = min(max(i0, 0), size - 1);
+  c1 = min(max(i0 + 1, 0), size - 1);
+}
+LP_DEVICE int lp_taps_i32(const LpGrid& g, int C, int b, float x, float y, float z, int* off, float* w) {
+  if (g.kind == LP_VOXEL) {
+    int x0, y0, z0, cx[2], cy[2], cz[2];
+    float fx, fy, fz, wx[2], wy[2], wz[2];
+    lp_axis_i(x, g.W, x0, fx); lp_axis_i(y, g.H, y0, fy); lp_axis_i(z, g.D, z0, fz);
+    lp_corner_i(x0, fx, g.W, wx[0], wx[1], cx[0], cx[1]);
+    lp_corner_i(y0, fy, g.H, wy[0], wy[1], cy[0], cy[1]);
+    lp_corner_i(z0, fz, g.D, wz[0], wz[1], cz[0], cz[1]);
+    const int bbase = (int)g.base + b * g.D * g.H * g.W * C;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      w[c] = wx[c & 1] * wy[(c >> 1) & 1] * wz[(c >> 2) & 1];
+      off[c] = bbase + ((cz[(c >> 2) & 1] * g.H + cy[(c >> 1) & 1]) * g.W + cx[c & 1]) * C;
+    }
+    return 8;
+  }
+  float u, v;
+  int U, V;
+  if (g.kind == LP_PLANE_XY) { u = x; v = y; U = g.W; V = g.H; }
+  else if (g.kind == LP_PLANE_XZ) { u = x; v = z; U = g.W; V = g.D; }
+  else { u = y; v = z; U = g.H; V = g.D; }
+  int u0, v0, cu[2], cv[2];
+  float fu, fv, wu[2], wv[2];
+  lp_axis_i(u, U, u0, fu); lp_axis_i(v, V, v0, fv);
+  lp_corner_i(u0, fu, U, wu[0], wu[1], cu[0], cu[1]);
+  lp_corner_i(v0, fv, V, wv[0], wv[1], cv[0], cv[1]);
+  const int bbase = (int)g.base + b * U * V * C;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    w[c] = wu[c & 1] * wv[c >> 1];
+    off[c] = bbase + (cv[c >> 1] * U + cu[c & 1]) * C;
+  }
+  return 4;
+}
 
 constexpr int GT = 128;  // threads = rays per group (the MMA's M)
 
@@ -116,7 +221,7 @@ LP_DEVICE void lp_gather_regs(const LpGridSet& G, int b, float x, float y, float
   for (int gi = 0; gi < G.n; ++gi) {
     int off[8];
     float w[8];
-    const int nt = lpf::lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
+    const int nt = lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
     float wsum = 0.f;
 #pragma unroll
     for (int tp = 0; tp < 8; ++tp)
@@ -148,7 +253,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
                                                                    float* __restrict__ out_feat, int feat_stride) {
   using I = Img<C>;
   LP_DYN_SMEM(unsigned char, sm);
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int grp = tid / GT, ngroups = blockDim.x / GT, wig = (tid >> 5) & 3;  // warp in group = TMEM lane quarter
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + I::FWD_END);  // one per group
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
@@ -175,7 +280,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
   const int tot = M.S + M.S_inf;
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
-    const Ray1 me = lpf::lp_load_ray1(R, tile * GT + (tid % GT), G.g[0].B);
+    const Ray1 me = lp_load_ray1(R, tile * GT + (tid % GT), G.g[0].B);
     {  // stage the ray encoding once (columns TC_E..): A operand of the colour layer's second half
       float e[32];
       const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)(me.active ? me.ray : R.n - 1) * H);
@@ -189,9 +294,9 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
     float nlt = 0.f, T = 1.f, acc_len = 0.f, acc_c[3] = {0.f, 0.f, 0.f};
 
     for (int step = 0; step < tot; ++step) {
-      const Sched sc = lpf::lp_sched(step, M);
+      const Sched sc = lp_sched(step, M);
       float depth, delta;
-      lpf::lp_depth_delta(sc, me.near, me.far, depth, delta);
+      lp_depth_delta(sc, me.near, me.far, depth, delta);
       {
         float x = me.ox + depth * me.dx, y = me.oy + depth * me.dy, z = me.oz + depth * me.dz;
         if (M.contract) lp_contract(x, y, z);
@@ -277,15 +382,43 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
   if (tid < 32) lp_tmem_dealloc512(*tmem_slot);
 }
 
+// -------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------
+static inline bool lp_tc_render_supported(const LpRenderArgs& a) {
+  const LpDecoder& D = a.D;
+  if (D.use_color_grid || a.use_scaffold) return false;
+  if (D.trunk.n_layers != 2 || D.opacity.n_layers != 2 || D.color.n_layers != 2) return false;
+  if (D.C != 16 && D.C != 32) return false;
+  if (D.n_feat > 3 || D.in_c != lptc::H) return false;
+  const LpLayer* ls[4] = {&D.trunk.l[0], &D.trunk.l[1], &D.opacity.l[0], &D.color.l[0]};
+  for (int i = 0; i < 4; ++i)
+    if (ls[i]->N != lptc::H) return false;
+  return true;
+}
+
+#ifdef LP_HOSTSIM
+#define LP_TC_SET_SMEM(kernel, bytes) 0
+static inline int lp_tc_num_sms() { return 2; }
+#else
+#define LP_TC_SET_SMEM(kernel, bytes) \
+  (cudaFuncSetAttribute((kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)) != cudaSuccess)
+static inline int lp_tc_num_sms() {
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+#endif
+
 template <int C>
 static int lp_tc_render_forward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, float* out_len, float* out_nlt,
                                   float* out_feat, int feat_stride) {
   const int groups = 4;
   const size_t bytes = Img<C>::FWD_END + 128;
-  if (LP_FAST_SET_SMEM(lp_render_fwd_tc_kernel<C>, bytes)) return LP_ERR_CUDA;
+  if (LP_TC_SET_SMEM(lp_render_fwd_tc_kernel<C>, bytes)) return LP_ERR_CUDA;
   const int tiles = (a.R.n + GT - 1) / GT;
   int blocks = (tiles + groups - 1) / groups;
-  const int max_blocks = lp_fast_num_sms();  // persistent; one CTA per SM owns its tensor memory
+  const int max_blocks = lp_tc_num_sms();  // persistent; one CTA per SM owns its tensor memory
   if (blocks > max_blocks) blocks = max_blocks;
   LP_LAUNCH(lp_render_fwd_tc_kernel<C>, dim3(blocks), dim3(groups * GT), bytes, st, a.R, a.M, a.D, a.G, params, out_len,
             out_nlt, out_feat, feat_stride);
@@ -410,7 +543,7 @@ LP_DEVICE void lp_splat_regs(const LpGridSet& G, float* grad, int b, float x, fl
   for (int gi = 0; gi < G.n; ++gi) {
     int off[8];
     float w[8];
-    const int nt = lpf::lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
+    const int nt = lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
     float wsum = 0.f;
 #pragma unroll
     for (int tp = 0; tp < 8; ++tp)
@@ -499,7 +632,7 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
 #define LP_TC_ROUND(ISSUE) LP_TC_HANDOFF(ISSUE) LP_TC_WAIT()
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
-    const Ray1 me = lpf::lp_load_ray1(R, tile * GT + s, G.g[0].B);
+    const Ray1 me = lp_load_ray1(R, tile * GT + s, G.g[0].B);
     const int q = me.active ? me.ray : R.n - 1;
     {
       float e[32];
@@ -530,8 +663,8 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
     struct Pos { float depth, delta, x, y, z, oob; };
     auto sample_at = [&](int step) {
       Pos p;
-      const Sched sc = lpf::lp_sched(step, M);
-      lpf::lp_depth_delta(sc, me.near, me.far, p.depth, p.delta);
+      const Sched sc = lp_sched(step, M);
+      lp_depth_delta(sc, me.near, me.far, p.depth, p.delta);
       p.x = me.ox + p.depth * me.dx; p.y = me.oy + p.depth * me.dy; p.z = me.oz + p.depth * me.dz;
       if (M.contract) lp_contract(p.x, p.y, p.z);
       p.oob = M.mask_oob ? lp_in_bounds(p.x, p.y, p.z) : 1.f;
@@ -729,10 +862,10 @@ template <int C>
 static int lp_tc_render_backward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
   const int groups = 2;
   const size_t bytes = BImg<C>::GROUPS + (size_t)groups * BImg<C>::GROUP_BYTES;
-  if (LP_FAST_SET_SMEM(lp_render_bwd_tc_kernel<C>, bytes)) return LP_ERR_CUDA;
+  if (LP_TC_SET_SMEM(lp_render_bwd_tc_kernel<C>, bytes)) return LP_ERR_CUDA;
   const int tiles = (a.R.n + GT - 1) / GT;
   int blocks = (tiles + groups - 1) / groups;
-  const int max_blocks = lp_fast_num_sms();
+  const int max_blocks = lp_tc_num_sms();
   if (blocks > max_blocks) blocks = max_blocks;
   LP_LAUNCH(lp_render_bwd_tc_kernel<C>, dim3(blocks), dim3(groups * GT), bytes, st, a.R, a.M, a.D, a.G, params, io);
   return LP_OK;

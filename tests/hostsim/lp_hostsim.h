@@ -57,9 +57,6 @@ struct WarpCtx {
   std::barrier<>* bar;
   uint32_t slots_u[32];
   int pred[32];
-  float mma_a[32 * 4];
-  float mma_b[32 * 2];
-  void* mma;
 };
 
 struct BlockCtx {
@@ -208,35 +205,8 @@ static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f
 static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
 
-// mma.sync.m16n8k8 TF32 emulation: every lane publishes its fragments, then computes its own four
-// outputs from the assembled 16x8 / 8x8 operands.  Operands are truncated to TF32 (19 bits) the
-// way the tensor core reads them, so precision tests are meaningful here too.
 static inline float lp_hs_trunc_tf32(float x) {
   unsigned u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; float y; std::memcpy(&y, &u, 4); return y;
-}
-static inline void lp_hostsim_mma_m16n8k8(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
-  auto* w = lp_hostsim::g_ctx->warp;
-  const int lane = lp_hostsim::g_ctx->lane;
-  float (*A)[4] = reinterpret_cast<float (*)[4]>(w->mma_a);
-  float (*B)[2] = reinterpret_cast<float (*)[2]>(w->mma_b);
-  for (int i = 0; i < 4; ++i) A[lane][i] = lp_hs_trunc_tf32(a[i]);
-  for (int i = 0; i < 2; ++i) B[lane][i] = lp_hs_trunc_tf32(b[i]);
-  w->bar->arrive_and_wait();
-  const int g = lane >> 2, t = lane & 3;
-  auto Aat = [&](int row, int k) -> float {  // row 0..15, k 0..7
-    int gg = row & 7, hi_row = row >> 3, tt = k & 3, hi_k = k >> 2;
-    return A[gg * 4 + tt][hi_row + 2 * hi_k];
-  };
-  auto Bat = [&](int k, int n) -> float { return B[n * 4 + (k & 3)][k >> 2]; };
-  float out[4];
-  for (int i = 0; i < 4; ++i) {
-    int row = g + 8 * (i >> 1), col = 2 * t + (i & 1);
-    float acc = d[i];
-    for (int k = 0; k < 8; ++k) acc += Aat(row, k) * Bat(k, col);
-    out[i] = acc;
-  }
-  w->bar->arrive_and_wait();
-  for (int i = 0; i < 4; ++i) d[i] = out[i];
 }
 
 // ---- emulation of the tcgen05 / mbarrier layer of lp_platform.cuh (protocol + layout logic) ----
@@ -256,37 +226,10 @@ static inline float lp_hs_bf16(const unsigned char* base, int byte_off) {
   unsigned short h; std::memcpy(&h, base + byte_off, 2);
   unsigned u = (unsigned)h << 16; float f; std::memcpy(&f, &u, 4); return f;
 }
-// the MMA executes synchronously (program order == issue order, like the in-order tensor pipe)
-static inline void lp_tc_mma_bf16(unsigned tmem_base, int col, const void* a, const void* b, int n, int accumulate) {
-  static std::mutex mu;  // several warps may issue concurrently; the real pipe serialises them
-  std::lock_guard<std::mutex> lk(mu);
-  float* T = lp_hostsim::g_ctx->block->tmem;
-  const unsigned char* A = static_cast<const unsigned char*>(a);
-  const unsigned char* B = static_cast<const unsigned char*>(b);
-  auto off = [](int mn, int k) { return (mn / 8) * 512 + (k / 8) * 128 + (k % 8) * 16 + (mn % 8) * 2; };
-  for (int m = 0; m < 128; ++m)
-    for (int j = 0; j < n; ++j) {
-      float acc = accumulate ? T[m * 512 + tmem_base + col + j] : 0.f;
-      for (int k = 0; k < 16; ++k) acc += lp_hs_bf16(A, off(m, k)) * lp_hs_bf16(B, off(j, k));
-      T[m * 512 + tmem_base + col + j] = acc;
-    }
-}
+// MMAs execute synchronously (program order == issue order, like the in-order tensor pipe)
 static inline void lp_tc_commit(unsigned long long* bar) {
   std::atomic_ref<unsigned long long>(*bar).fetch_add(1, std::memory_order_release);
 }
-static inline void lp_tmem_ld32(unsigned tmem_base, int lane_base, int col, float (&v)[32]) {
-  const float* T = lp_hostsim::g_ctx->block->tmem;
-  const int row = lane_base + lp_hostsim::g_ctx->lane;
-  for (int j = 0; j < 32; ++j) v[j] = T[row * 512 + tmem_base + col + j];
-}
-
-static inline unsigned lp_tc_desc_lo(const void*) { return 0; }
-static inline void lp_tc_mma_bf16_off(unsigned tmem_base, int col, unsigned, const void* base, int a_off, int b_off, int n,
-                                      int accumulate) {
-  const unsigned char* b = static_cast<const unsigned char*>(base);
-  lp_tc_mma_bf16(tmem_base, col, b + a_off, b + b_off, n, accumulate);
-}
-
 // ---- TS MMAs / tcgen05.st / named barriers (see lp_platform.cuh); TMEM words hold raw 32-bit patterns ----
 static inline unsigned lp_hs_tmem_word(int lane, int col) {
   unsigned u; std::memcpy(&u, &lp_hostsim::g_ctx->block->tmem[lane * 512 + col], 4); return u;
