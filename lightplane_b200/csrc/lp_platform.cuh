@@ -150,14 +150,34 @@ LP_DEVICE void lp_tc_mma_ss_mn(unsigned d_taddr, lp_kdesc_t a_lo, lp_kdesc_t b_l
 // warp-collective: lane i writes NW consecutive columns of TMEM lane 32*(warp%4)+i
 template <int NW>
 LP_DEVICE void lp_tmem_st(unsigned taddr, const unsigned (&v)[NW]) {
-  static_assert(NW == 8 || NW == 16, "8 or 16 columns");
-  if (NW == 8)
+  static_assert(NW == 4 || NW == 8 || NW == 16 || NW == 32, "4, 8, 16 or 32 columns");
+  if constexpr (NW == 32) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+        "%24, %25, %26, %27, %28, %29, %30, %31};" ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+        "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
+        "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]), "r"(taddr) : "memory");
+  } else if constexpr (NW == 4)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0, %1, %2, %3};" ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(taddr) : "memory");
+  else if constexpr (NW == 8)
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::"r"(v[0]), "r"(v[1]), "r"(v[2]),
                  "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(taddr) : "memory");
   else
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
                  ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
                  "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(taddr) : "memory");
+}
+// clear N columns of this thread's TMEM lane (accumulators are pre-zeroed so that every MMA accumulates
+// and the MMAs of one product can be issued by several threads in any order)
+template <int N>
+LP_DEVICE void lp_tmem_zero(unsigned taddr) {
+  unsigned z[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) z[j] = 0u;
+  lp_tmem_st<N>(taddr, z);
 }
 LP_DEVICE void lp_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // this thread's TMEM address for column `col`: lanes 32*(warp%4).. of the CTA's allocation
@@ -179,6 +199,31 @@ LP_DEVICE void lp_tmem_ld32u(unsigned taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+// warp-collective: lane i receives N consecutive columns of its TMEM lane
+template <int N>
+LP_DEVICE void lp_tmem_ld(unsigned taddr, float (&v)[N]) {
+  static_assert(N == 8 || N == 16 || N == 32, "8, 16 or 32 columns");
+  if constexpr (N == 32) {
+    lp_tmem_ld32u(taddr, v);
+  } else if constexpr (N == 16) {
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  } else {
+    unsigned r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+  }
 }
 // named barrier over `nthreads` threads (ids 1..15; 0 is __syncthreads)
 LP_DEVICE void lp_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }

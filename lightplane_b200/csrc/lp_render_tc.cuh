@@ -199,7 +199,11 @@ LP_DEVICE void lp_stage_row(unsigned taddr_a, const float (&x)[N]) {
 // per-group tensor-memory columns (forward): A hi 0..15 / lo 16..31, encoding hi 32..47 / lo 48..63, D 64..127
 constexpr int TC_A = 0, TC_E = 32, TC_D = 64, TC_GROUP_COLS = 128;
 
-// leader thread: D(n columns) = A(K) x W, three bf16 products per 16-wide k-step
+// leader thread: D(n columns) = A(K) x W, three bf16 products per 16-wide k-step.
+// (One thread issues a tcgen05.mma every ~46 cycles while the pipe needs 16 for N = 32; dealing the
+// MMAs of a product to several issuing threads -- legal once the accumulator is pre-cleared so that all
+// of them accumulate -- reaches the pipe rate in isolation (tools/tc_test2.cu) but made the kernels
+// slower: 84.7 vs 75.9 ms backward.  The chain is not bound by MMA issue.)
 LP_DEVICE void lp_issue_layer(unsigned tbase, int d_col, int a_col, lp_kdesc_t whi, lp_kdesc_t wlo, int ksteps, int k0,
                               int nstride, int n, bool first, int lo_off = 16) {
 #pragma unroll
@@ -214,10 +218,15 @@ LP_DEVICE void lp_issue_layer(unsigned tbase, int d_col, int a_col, lp_kdesc_t w
 }
 
 // the owner thread samples all C channels of its sample point into registers
-template <int C>
-LP_DEVICE void lp_gather_regs(const LpGridSet& G, int b, float x, float y, float z, float oob, float (&acc)[C]) {
+// (CW channels starting at ch0: a sample's channels may be split over several threads)
+template <int C, int CW = C>
+LP_DEVICE void lp_gather_regs(const LpGridSet& G, int b, float x, float y, float z, float oob, float (&acc)[CW], int ch0 = 0) {
 #pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  for (int c = 0; c < CW; ++c) acc[c] = 0.f;
+#ifdef LP_ABL_NO_MEM
+  acc[0] = x * y + z;
+  return;
+#endif
   for (int gi = 0; gi < G.n; ++gi) {
     int off[8];
     float w[8];
@@ -231,8 +240,8 @@ LP_DEVICE void lp_gather_regs(const LpGridSet& G, int b, float x, float y, float
     for (int tp = 0; tp < 8; ++tp) {
       if (tp < nt) {
 #pragma unroll
-        for (int k = 0; k < C / 4; ++k) {
-          const float4 v = lp_ldg4(G.data + off[tp] + 4 * k);
+        for (int k = 0; k < CW / 4; ++k) {
+          const float4 v = lp_ldg4(G.data + off[tp] + ch0 + 4 * k);
           acc[4 * k] = fmaf(w[tp], v.x, acc[4 * k]); acc[4 * k + 1] = fmaf(w[tp], v.y, acc[4 * k + 1]);
           acc[4 * k + 2] = fmaf(w[tp], v.z, acc[4 * k + 2]); acc[4 * k + 3] = fmaf(w[tp], v.w, acc[4 * k + 3]);
         }
@@ -240,7 +249,7 @@ LP_DEVICE void lp_gather_regs(const LpGridSet& G, int b, float x, float y, float
     }
   }
 #pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] *= oob;
+  for (int c = 0; c < CW; ++c) acc[c] *= oob;
 }
 
 // ===========================================================================================
@@ -458,7 +467,8 @@ struct BImg {
   static constexpr int A2 = A1 + (ONES1 + 1) * 2048;
   static constexpr int DY = A2 + 9 * 2048;
   static constexpr int DYL = DY + 16 * 2048;
-  static constexpr int GROUP_BYTES = DYL + 2 * 2048;
+  static constexpr int XCH = DYL + 2 * 2048;     // float4 [2][128]: partial output-layer sums of the two threads of a sample
+  static constexpr int GROUP_BYTES = XCH + 4096;
   static_assert(A2 + 16 * 2048 <= GROUP_BYTES, "operand window leaves the group's region");
 };
 // tensor-memory columns: per group A (hi 0..31, lo 32..63), encoding (hi 64..79, lo 80..95), D 96..159;
@@ -482,6 +492,9 @@ LP_DEVICE void lp_build_bimg(unsigned char* sm, const float* __restrict__ P, con
 // this thread's sample s: features 8*chunk .. 8*chunk+7 of a tile
 LP_DEVICE void lp_tile8(unsigned char* tile, int chunk, int s, float x0, float x1, float x2, float x3, float x4, float x5,
                         float x6, float x7) {
+#ifdef LP_ABL_NO_TILES
+  return;
+#endif
   *reinterpret_cast<uint4*>(tile + chunk * 2048 + (s >> 3) * 128 + (s & 7) * 16) =
       make_uint4(lp_pack_bf16x2(x0, x1), lp_pack_bf16x2(x2, x3), lp_pack_bf16x2(x4, x5), lp_pack_bf16x2(x6, x7));
 }
@@ -501,10 +514,10 @@ LP_DEVICE unsigned lp_mask_pos(const float (&x)[N]) {
 
 // ReLU gate read back from the bf16 operand tile the activation was written to (this thread's own row;
 // an activation is > 0 iff its bf16 image is non-zero): x[j] survives iff feature j of the tile row != 0
-template <bool MULT_FIRST = false>
-LP_DEVICE void lp_gate_row(float (&x)[32], const unsigned char* tile, int chunk0, int s) {
+template <int N>
+LP_DEVICE void lp_gate_row(float (&x)[N], const unsigned char* tile, int chunk0, int s) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < N / 8; ++c) {
     const uint4 w = *reinterpret_cast<const uint4*>(tile + (chunk0 + c) * 2048 + (s >> 3) * 128 + (s & 7) * 16);
     const unsigned ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -517,29 +530,36 @@ LP_DEVICE void lp_gate_row(float (&x)[32], const unsigned char* tile, int chunk0
 
 // leader: the group's parameter-gradient products over its 128 samples (8 k-steps of 16)
 template <int C>
-LP_DEVICE void lp_issue_dw(unsigned tmem, unsigned char* gs, int accumulate) {
+LP_DEVICE void lp_issue_dw(unsigned tmem, unsigned char* gs, int accumulate, int wi = 0, int nw = 1) {
   using B = BImg<C>;
   const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), a2 = lp_tc_mndesc_lo(gs + B::A2), dy = lp_tc_mndesc_lo(gs + B::DY),
                    dyl = lp_tc_mndesc_lo(gs + B::DYL);
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    lp_tc_mma_ss_mn(tmem + BT_W, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 128, accumulate | (ks > 0));
-    lp_tc_mma_ss_mn(tmem + BT_L, lp_tc_kadv(a2, ks * 256), lp_tc_kadv(dyl, ks * 256), 2048, 16, accumulate | (ks > 0));
+    if ((2 * ks) % nw == wi)
+      lp_tc_mma_ss_mn(tmem + BT_W, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 128, accumulate | (ks > 0));
+    if ((2 * ks + 1) % nw == wi)
+      lp_tc_mma_ss_mn(tmem + BT_L, lp_tc_kadv(a2, ks * 256), lp_tc_kadv(dyl, ks * 256), 2048, 16, accumulate | (ks > 0));
   }
 }
 // encoding^T x (step-sum of the colour-hidden gradient): A1 chunks 0-3 hold the encodings, DY chunks 8-11 the sums
 template <int C>
-LP_DEVICE void lp_issue_encw(unsigned tmem, unsigned char* gs, int accumulate) {
+LP_DEVICE void lp_issue_encw(unsigned tmem, unsigned char* gs, int accumulate, int wi = 0, int nw = 1) {
   using B = BImg<C>;
   const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), dy = lp_tc_mndesc_lo(gs + B::DY + 8 * 2048);
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks)
-    lp_tc_mma_ss_mn(tmem + BT_ENC, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 32, accumulate | (ks > 0));
+    if (ks % nw == wi)
+      lp_tc_mma_ss_mn(tmem + BT_ENC, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 32, accumulate | (ks > 0));
 }
 
 // adjoint of lp_gather_regs: the owner thread scatters its row into the grid gradient
-template <int C>
-LP_DEVICE void lp_splat_regs(const LpGridSet& G, float* grad, int b, float x, float y, float z, const float (&d)[C]) {
+template <int C, int CW = C>
+LP_DEVICE void lp_splat_regs(const LpGridSet& G, float* grad, int b, float x, float y, float z, const float (&d)[CW], int ch0 = 0) {
+#ifdef LP_ABL_NO_MEM
+  if (d[0] == 1.2345f) grad[0] = x;
+  return;
+#endif
   for (int gi = 0; gi < G.n; ++gi) {
     int off[8];
     float w[8];
@@ -554,32 +574,45 @@ LP_DEVICE void lp_splat_regs(const LpGridSet& G, float* grad, int b, float x, fl
       if (tp < nt) {
         const bool on = w[tp] != 0.f;
 #pragma unroll
-        for (int k = 0; k < C / 4; ++k)
-          lp_red_add4_if(on, grad + off[tp] + 4 * k, w[tp] * d[4 * k], w[tp] * d[4 * k + 1], w[tp] * d[4 * k + 2],
+        for (int k = 0; k < CW / 4; ++k)
+          lp_red_add4_if(on, grad + off[tp] + ch0 + 4 * k, w[tp] * d[4 * k], w[tp] * d[4 * k + 1], w[tp] * d[4 * k + 2],
                          w[tp] * d[4 * k + 3]);
       }
     }
   }
 }
 
-template <int C>
-__global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
-                                                                   const float* __restrict__ params, LpBwdIo io) {
+#ifdef LP_ABL_NO_DW
+#define LP_ABL_DW(x)
+#else
+#define LP_ABL_DW(x) x
+#endif
+// NP threads per sample: thread part h of sample s owns columns [W*h, W*h + W) of every 32-wide
+// activation / gradient row (W = 32/NP) and channels [CW*h, ..) of the grid features (CW = C/NP); both
+// parts address the same TMEM lane (warps w and w+4 of a group share a lane quarter).  NP = 2 halves the
+// per-thread work and registers, doubling the warps that hide the tensor-core round trips, at the
+// price of duplicated ray/tap/compositing arithmetic and one exchange of the output layer's partial sums.
+template <int C, int NP>
+__global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
+                                                                        const float* __restrict__ params, LpBwdIo io) {
   using I = Img<C>;
   using B = BImg<C>;
+  constexpr int W = 32 / NP, CW = C / NP, GTH = GT * NP;
   LP_DYN_SMEM(unsigned char, sm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = tid / GT, ngroups = blockDim.x / GT, wig = warp & 3, s = tid % GT;  // s = sample row in the group
+  const int grp = tid / GTH, ngroups = blockDim.x / GTH, tg = tid % GTH;
+  const int s = tg % GT, h = tg / GT, wig = (tg >> 5) & 3;  // sample row, column part, TMEM lane quarter
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + B::BARS);  // [2g] round trips, [2g+1] dW; [8] init
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 10);
   unsigned char* gs = sm + B::GROUPS + grp * B::GROUP_BYTES;
   lp_build_img<C>(sm, params, D);
   lp_build_bimg<C>(sm, params, D);
-  for (int e = s; e < B::GROUP_BYTES / 16; e += GT) reinterpret_cast<uint4*>(gs)[e] = make_uint4(0u, 0u, 0u, 0u);
+  for (int e = tg; e < B::GROUP_BYTES / 16; e += GTH) reinterpret_cast<uint4*>(gs)[e] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
-  // rows of ones (bf16 1.0): first row of A1 chunk ONES1 and of A2 chunk 8
-  *reinterpret_cast<unsigned short*>(gs + B::A1 + B::ONES1 * 2048 + (s >> 3) * 128 + (s & 7) * 16) = 0x3F80;
-  *reinterpret_cast<unsigned short*>(gs + B::A2 + 8 * 2048 + (s >> 3) * 128 + (s & 7) * 16) = 0x3F80;
+  if (h == 0) {  // rows of ones (bf16 1.0): first row of A1 chunk ONES1 and of A2 chunk 8
+    *reinterpret_cast<unsigned short*>(gs + B::A1 + B::ONES1 * 2048 + (s >> 3) * 128 + (s & 7) * 16) = 0x3F80;
+    *reinterpret_cast<unsigned short*>(gs + B::A2 + 8 * 2048 + (s >> 3) * 128 + (s & 7) * 16) = 0x3F80;
+  }
   if (tid == 0) {
     for (int i = 0; i < 9; ++i) lp_mbar_init(bars + i, 1);
     lp_mbar_init_fence();
@@ -601,8 +634,10 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
 
   const unsigned tbase = tmem + (unsigned)(grp * BT_GROUP_COLS);
   const unsigned tme = lp_taddr(tbase, wig, 0);
-  const bool leader = s == 0;
+  const bool leader = tg == 0;
   const float* F = reinterpret_cast<const float*>(sm + I::F32);
+  float4* xch = reinterpret_cast<float4*>(gs + B::XCH);
+  const int pk = (W / 2) * h, fc = W * h, ck = (W / 8) * h;  // packed-column / fp32-column / tile-chunk offset of this part
   const lp_kdesc_t w_t0h = lp_tc_kdesc_lo(sm + I::T0_HI), w_t0l = lp_tc_kdesc_lo(sm + I::T0_LO),
                    w_t1h = lp_tc_kdesc_lo(sm + I::T1_HI), w_t1l = lp_tc_kdesc_lo(sm + I::T1_LO),
                    w_och = lp_tc_kdesc_lo(sm + I::OC_HI), w_ocl = lp_tc_kdesc_lo(sm + I::OC_LO),
@@ -617,10 +652,14 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
   // A round trip to the tensor core is split in two so that independent work can run while the MMAs
   // execute: HANDOFF publishes this thread's staged operand row and lets the leader issue (ISSUE ends
   // with the commit to `bar`); WAIT blocks until the result is in tensor memory.
+#ifdef LP_ABL_NO_SYNC  // profiling only (results are garbage): no hand-off, no MMAs, no waits
+#define LP_TC_HANDOFF(ISSUE)
+#define LP_TC_WAIT()
+#else
 #define LP_TC_HANDOFF(ISSUE)               \
   lp_tmem_wait_st();                       \
   lp_tc_fence_before();                    \
-  lp_bar_sync(1 + grp, GT);                \
+  lp_bar_sync(1 + grp, GTH);               \
   if (leader) {                            \
     lp_tc_fence_after();                   \
     ISSUE;                                 \
@@ -629,20 +668,21 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
   lp_mbar_wait(bar, phase);                \
   phase ^= 1;                              \
   lp_tc_fence_after();
+#endif
 #define LP_TC_ROUND(ISSUE) LP_TC_HANDOFF(ISSUE) LP_TC_WAIT()
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
     const Ray1 me = lp_load_ray1(R, tile * GT + s, G.g[0].B);
     const int q = me.active ? me.ray : R.n - 1;
     {
-      float e[32];
-      const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)q * H);
+      float e[W];
+      const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)q * H + fc);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < W / 4; ++k) {
         const float4 v = __ldg(e4 + k);
         e[4 * k] = v.x; e[4 * k + 1] = v.y; e[4 * k + 2] = v.z; e[4 * k + 3] = v.w;
       }
-      lp_stage_row<32, 16>(tme + BT_E, e);
+      lp_stage_row<W, 16>(tme + BT_E + pk, e);
     }
     // per-ray constants of the compositing gradient (renderer_bw.py:300-420)
     const float g_len = me.active ? io.g_len[q] : 0.f, g_nlt = me.active ? io.g_nlt[q] : 0.f;
@@ -653,9 +693,9 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
       if (c < D.n_feat) total = fmaf(gF[c], io.feat[(long long)q * io.feat_stride + c], total);
     }
     float nlt = 0.f, T = 1.f, prefix = 0.f;
-    float S[32];  // sum over steps of the colour-hidden gradient
+    float S[W];  // sum over steps of the colour-hidden gradient (this part's columns)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) S[j] = 0.f;
+    for (int j = 0; j < W; ++j) S[j] = 0.f;
 
     // Software pipeline across steps: the gather of step n+1 is issued while the tensor core runs the
     // first input-gradient product of step n, and the scatter of step n while it runs the first layer
@@ -671,49 +711,61 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
       return p;
     };
     Pos cur = sample_at(0), prev = cur;
-    float x0[C], dxp[C];  // gathered features of the current step; input gradient of the previous step
-    lp_gather_regs<C>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
+    float x0[CW], dxp[CW];  // gathered features of the current step; input gradient of the previous step
+    lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
     bool have_prev = false;
 
     for (int step = 0; step < tot; ++step) {
-      float v[32];
+      float v[W];
       // the previous step's parameter-gradient products must have consumed the tiles
+#ifndef LP_ABL_NO_SYNC
       if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
-      lp_tile_row<C>(gs + B::A1, 8, s, x0);
-      lp_stage_row<C, 32>(tme + BT_A, x0);
+#endif
+      lp_tile_row<CW>(gs + B::A1, 8 + (CW / 8) * h, s, x0);
+      lp_stage_row<CW, 32>(tme + BT_A + (CW / 2) * h, x0);
       // ------------------------------ forward recompute ------------------------------
       LP_TC_HANDOFF(lp_issue_layer(tbase, BT_D, BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, true, 32); lp_tc_commit(bar));
-      if (have_prev && me.active && prev.oob != 0.f) lp_splat_regs<C>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp);
+      if (have_prev && me.active && prev.oob != 0.f)
+        lp_splat_regs<C, CW>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp, CW * h);
       LP_TC_WAIT();
-      lp_tmem_ld32u(tme + BT_D, v);
+      lp_tmem_ld<W>(tme + BT_D + fc, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + j], 0.f);
-      lp_tile_row<32>(gs + B::A1, 0, s, v);
-      lp_stage_row<32, 32>(tme + BT_A, v);
+      for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j] + F[I::FB + fc + j], 0.f);
+      lp_tile_row<W>(gs + B::A1, 0 + ck, s, v);
+      lp_stage_row<W, 32>(tme + BT_A + pk, v);
       LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_t1h, w_t1l, 2, 0, 512, 32, true, 32); lp_tc_commit(bar));
-      lp_tmem_ld32u(tme + BT_D, v);
+      lp_tmem_ld<W>(tme + BT_D + fc, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + 32 + j], 0.f);
-      lp_tile_row<32>(gs + B::A1, 4, s, v);
-      lp_stage_row<32, 32>(tme + BT_A, v);
+      for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j] + F[I::FB + 32 + fc + j], 0.f);
+      lp_tile_row<W>(gs + B::A1, 4 + ck, s, v);
+      lp_stage_row<W, 32>(tme + BT_A + pk, v);
       LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_och, w_ocl, 2, 0, 1024, 64, true, 32);
                   lp_issue_layer(tbase, BT_D, BT_E, w_och, w_ocl, 2, 2, 1024, 64, false, 16); lp_tc_commit(bar));
-      float raw = F[I::FBL + 3], lg0 = F[I::FBL], lg1 = F[I::FBL + 1], lg2 = F[I::FBL + 2];
-      lp_tmem_ld32u(tme + BT_D, v);
+      float raw = 0.f, lg0 = 0.f, lg1 = 0.f, lg2 = 0.f;  // this part's share of the output layer
+      lp_tmem_ld<W>(tme + BT_D + fc, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = fmaxf(v[j] + F[I::FB + 64 + j], 0.f);
-        raw = fmaf(v[j], F[I::FWO + j], raw);
+      for (int j = 0; j < W; ++j) {
+        v[j] = fmaxf(v[j] + F[I::FB + 64 + fc + j], 0.f);
+        raw = fmaf(v[j], F[I::FWO + fc + j], raw);
       }
-      lp_tile_row<32>(gs + B::A2, 0, s, v);
-      lp_tmem_ld32u(tme + BT_D + 32, v);
+      lp_tile_row<W>(gs + B::A2, 0 + ck, s, v);
+      lp_tmem_ld<W>(tme + BT_D + 32 + fc, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = fmaxf(v[j] + F[I::FB + 96 + j], 0.f);
-        const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
+      for (int j = 0; j < W; ++j) {
+        v[j] = fmaxf(v[j] + F[I::FB + 96 + fc + j], 0.f);
+        const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * (fc + j));
         lg0 = fmaf(v[j], w.x, lg0); lg1 = fmaf(v[j], w.y, lg1); lg2 = fmaf(v[j], w.z, lg2);
       }
-      lp_tile_row<32>(gs + B::A2, 4, s, v);
+      lp_tile_row<W>(gs + B::A2, 4 + ck, s, v);
+      if (NP == 2) {  // combine the two parts' partial sums (both then run the same compositing arithmetic)
+        xch[h * GT + s] = make_float4(lg0, lg1, lg2, raw);
+#ifndef LP_ABL_NO_SYNC
+        lp_bar_sync(1 + grp, GTH);
+#endif
+        const float4 o = xch[(h ^ 1) * GT + s];
+        lg0 += o.x; lg1 += o.y; lg2 += o.z; raw += o.w;
+      }
+      raw += F[I::FBL + 3]; lg0 += F[I::FBL]; lg1 += F[I::FBL + 1]; lg2 += F[I::FBL + 2];
       // ------------------------------ compositing gradient ------------------------------
       float g_raw, dl0, dl1, dl2;
       {
@@ -732,72 +784,75 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
         dl1 = w * gF[1] * s1 * (1.f - s1);
         dl2 = w * gF[2] * s2 * (1.f - s2);
       }
-      lp_tile8(gs + B::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
+      if (h == 0) lp_tile8(gs + B::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
       // ------------------------------ backward sweep ------------------------------
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = g_raw * F[I::FWO + j];  // d_ho
-      lp_gate_row(v, gs + B::A2, 0, s);
-      lp_tile_row<32>(gs + B::DY, 4, s, v);
-      lp_stage_row<32, 32>(tme + BT_A, v);
+      for (int j = 0; j < W; ++j) v[j] = g_raw * F[I::FWO + fc + j];  // d_ho
+      lp_gate_row<W>(v, gs + B::A2, 0 + ck, s);
+      lp_tile_row<W>(gs + B::DY, 4 + ck, s, v);
+      lp_stage_row<W, 32>(tme + BT_A + pk, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {                                                         // d_hc
-        const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
+      for (int j = 0; j < W; ++j) {                                     // d_hc
+        const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * (fc + j));
         v[j] = fmaf(dl0, w.x, fmaf(dl1, w.y, dl2 * w.z));
       }
-      lp_gate_row(v, gs + B::A2, 4, s);
+      lp_gate_row<W>(v, gs + B::A2, 4 + ck, s);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) S[j] += v[j];
-      lp_tile_row<32>(gs + B::DY, 8, s, v);
-      lp_stage_row<32, 32>(tme + BT_A + 16, v);
+      for (int j = 0; j < W; ++j) S[j] += v[j];
+      lp_tile_row<W>(gs + B::DY, 8 + ck, s, v);
+      lp_stage_row<W, 32>(tme + BT_A + 16 + pk, v);
       LP_TC_HANDOFF(lp_issue_layer(tbase, BT_D, BT_A, w_xth, w_xtl, 4, 0, 1024, 32, true, 32); lp_tc_commit(bar));
       prev = cur;
       if (step + 1 < tot) {  // prefetch the next step's features while the product runs
         cur = sample_at(step + 1);
-        lp_gather_regs<C>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
+        lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
       }
       LP_TC_WAIT();
-      lp_tmem_ld32u(tme + BT_D, v);
-      lp_gate_row(v, gs + B::A1, 4, s);  // d_t
-      lp_tile_row<32>(gs + B::DY, 0, s, v);
-      lp_stage_row<32, 32>(tme + BT_A, v);
+      lp_tmem_ld<W>(tme + BT_D + fc, v);
+      lp_gate_row<W>(v, gs + B::A1, 4 + ck, s);  // d_t
+      lp_tile_row<W>(gs + B::DY, 0 + ck, s, v);
+      lp_stage_row<W, 32>(tme + BT_A + pk, v);
       LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_xhh, w_xhl, 2, 0, 512, 32, true, 32); lp_tc_commit(bar));
-      lp_tmem_ld32u(tme + BT_D, v);
-      lp_gate_row(v, gs + B::A1, 0, s);  // d_h1
-      lp_tile_row<32>(gs + B::DY, 12, s, v);
-      lp_stage_row<32, 32>(tme + BT_A, v);
+      lp_tmem_ld<W>(tme + BT_D + fc, v);
+      lp_gate_row<W>(v, gs + B::A1, 0 + ck, s);  // d_h1
+      lp_tile_row<W>(gs + B::DY, 12 + ck, s, v);
+      lp_stage_row<W, 32>(tme + BT_A + pk, v);
       lp_fence_async_smem();  // this step's tile writes -> visible to the tensor core
       LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_x0h, w_x0l, 2, 0, 512, C, true, 32); lp_tc_commit(bar);
-                  lp_issue_dw<C>(tmem, gs, 1); lp_tc_commit(bar_dw));
+                  LP_ABL_DW(lp_issue_dw<C>(tmem, gs, 1)); lp_tc_commit(bar_dw));
       ++n_dw;
-      lp_tmem_ld32u(tme + BT_D, v);
+      lp_tmem_ld<CW>(tme + BT_D + CW * h, dxp);
 #pragma unroll
-      for (int c = 0; c < C; ++c) dxp[c] = v[c] * prev.oob;
+      for (int c = 0; c < CW; ++c) dxp[c] *= prev.oob;
       have_prev = true;
     }
-    if (me.active && prev.oob != 0.f) lp_splat_regs<C>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp);  // last step's scatter
+    if (me.active && prev.oob != 0.f)  // last step's scatter
+      lp_splat_regs<C, CW>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp, CW * h);
     // ---- per-tile tail: encoding gradient = S Wc0^T, and the encoding's share of dWc0 = enc^T S ----
+#ifndef LP_ABL_NO_SYNC
     if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
+#endif
     {
-      float e[32];
-      const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)q * H);
+      float e[W];
+      const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)q * H + fc);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < W / 4; ++k) {
         const float4 vv = __ldg(e4 + k);
         e[4 * k] = vv.x; e[4 * k + 1] = vv.y; e[4 * k + 2] = vv.z; e[4 * k + 3] = vv.w;
       }
-      lp_tile_row<32>(gs + B::A1, 0, s, e);
-      lp_tile_row<32>(gs + B::DY, 8, s, S);
-      lp_stage_row<32, 32>(tme + BT_A + 16, S);  // K index 32..63 of the d_t weight tile = colour hidden
+      lp_tile_row<W>(gs + B::A1, 0 + ck, s, e);
+      lp_tile_row<W>(gs + B::DY, 8 + ck, s, S);
+      lp_stage_row<W, 32>(tme + BT_A + 16 + pk, S);  // K index 32..63 of the d_t weight tile = colour hidden
       lp_fence_async_smem();
-      float v[32];
+      float v[W];
       LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A + 16, w_xth, w_xtl, 2, 2, 1024, 32, true, 32); lp_tc_commit(bar);
                   lp_issue_encw<C>(tmem, gs, 1); lp_tc_commit(bar_dw));
       ++n_dw;
-      lp_tmem_ld32u(tme + BT_D, v);
+      lp_tmem_ld<W>(tme + BT_D + fc, v);
       if (me.active) {
-        float4* ge = reinterpret_cast<float4*>(io.g_enc + (long long)me.ray * H);
+        float4* ge = reinterpret_cast<float4*>(io.g_enc + (long long)me.ray * H + fc);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) ge[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        for (int k = 0; k < W / 4; ++k) ge[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
       }
     }
   }
@@ -805,7 +860,9 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
 #undef LP_TC_HANDOFF
 #undef LP_TC_WAIT
   // ---- drain, then the CTA's first four warps read the accumulators (TMEM lane = stack row) ----
+#ifndef LP_ABL_NO_SYNC
   if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
+#endif
   lp_tc_fence_before();
   __syncthreads();
   lp_tc_fence_after();
@@ -858,16 +915,20 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
   if (tid < 32) lp_tmem_dealloc512(tmem);
 }
 
+#ifndef LP_TC_BWD_NP
+#define LP_TC_BWD_NP 2  // threads per sample in the backward kernel
+#endif
 template <int C>
 static int lp_tc_render_backward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
   const int groups = 2;
+  constexpr int NP = LP_TC_BWD_NP;
   const size_t bytes = BImg<C>::GROUPS + (size_t)groups * BImg<C>::GROUP_BYTES;
-  if (LP_TC_SET_SMEM(lp_render_bwd_tc_kernel<C>, bytes)) return LP_ERR_CUDA;
+  if (LP_TC_SET_SMEM((lp_render_bwd_tc_kernel<C, NP>), bytes)) return LP_ERR_CUDA;
   const int tiles = (a.R.n + GT - 1) / GT;
   int blocks = (tiles + groups - 1) / groups;
   const int max_blocks = lp_tc_num_sms();
   if (blocks > max_blocks) blocks = max_blocks;
-  LP_LAUNCH(lp_render_bwd_tc_kernel<C>, dim3(blocks), dim3(groups * GT), bytes, st, a.R, a.M, a.D, a.G, params, io);
+  LP_LAUNCH((lp_render_bwd_tc_kernel<C, NP>), dim3(blocks), dim3(groups * GT * NP), bytes, st, a.R, a.M, a.D, a.G, params, io);
   return LP_OK;
 }
 static inline int lp_tc_render_backward(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {

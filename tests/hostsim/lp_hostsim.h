@@ -211,7 +211,9 @@ static inline float lp_hs_trunc_tf32(float x) {
 
 // ---- emulation of the tcgen05 / mbarrier layer of lp_platform.cuh (protocol + layout logic) ----
 // mbarrier: the 64-bit word counts completed phases (every barrier here expects one arrival).
-static inline void lp_mbar_init(unsigned long long* bar, int) { *bar = 0; }
+// mbarrier emulation: low 32 bits = completed phases, bits 32..47 = arrivals of the current phase,
+// bits 48..63 = expected arrivals per phase
+static inline void lp_mbar_init(unsigned long long* bar, int count) { *bar = (unsigned long long)count << 48; }
 static inline void lp_mbar_init_fence() {}
 static inline void lp_mbar_wait(unsigned long long* bar, int parity) {
   while ((int)(std::atomic_ref<unsigned long long>(*bar).load(std::memory_order_acquire) & 1ull) == parity)
@@ -228,7 +230,12 @@ static inline float lp_hs_bf16(const unsigned char* base, int byte_off) {
 }
 // MMAs execute synchronously (program order == issue order, like the in-order tensor pipe)
 static inline void lp_tc_commit(unsigned long long* bar) {
-  std::atomic_ref<unsigned long long>(*bar).fetch_add(1, std::memory_order_release);
+  std::atomic_ref<unsigned long long> a(*bar);
+  unsigned long long o = a.load(std::memory_order_acquire), n;
+  do {
+    const unsigned long long expect = o >> 48, arrived = ((o >> 32) & 0xffffull) + 1;
+    n = arrived == expect ? ((o & 0xffff0000ffffffffull) + 1) : (o + (1ull << 32));
+  } while (!a.compare_exchange_weak(o, n, std::memory_order_acq_rel));
 }
 // ---- TS MMAs / tcgen05.st / named barriers (see lp_platform.cuh); TMEM words hold raw 32-bit patterns ----
 static inline unsigned lp_hs_tmem_word(int lane, int col) {
@@ -295,11 +302,23 @@ static inline void lp_tmem_st(unsigned taddr, const unsigned (&v)[NW]) {
   const int row = (int)(taddr >> 16) + lp_hostsim::g_ctx->lane, col = taddr & 0xffff;
   for (int j = 0; j < NW; ++j) std::memcpy(&T[row * 512 + col + j], &v[j], 4);
 }
+template <int N>
+static inline void lp_tmem_zero(unsigned taddr) {
+  unsigned z[N];
+  for (int j = 0; j < N; ++j) z[j] = 0u;
+  lp_tmem_st<N>(taddr, z);
+}
 static inline void lp_tmem_wait_st() {}
 static inline void lp_tmem_ld32u(unsigned taddr, float (&v)[32]) {
   const float* T = lp_hostsim::g_ctx->block->tmem;
   const int row = (int)(taddr >> 16) + lp_hostsim::g_ctx->lane, col = taddr & 0xffff;
   for (int j = 0; j < 32; ++j) v[j] = T[row * 512 + col + j];
+}
+template <int N>
+static inline void lp_tmem_ld(unsigned taddr, float (&v)[N]) {
+  const float* T = lp_hostsim::g_ctx->block->tmem;
+  const int row = (int)(taddr >> 16) + lp_hostsim::g_ctx->lane, col = taddr & 0xffff;
+  for (int j = 0; j < N; ++j) v[j] = T[row * 512 + col + j];
 }
 static inline void lp_bar_sync(int id, int nthreads) {
   auto* b = lp_hostsim::g_ctx->block;

@@ -63,7 +63,7 @@ __host__ __device__ inline int kmajor_index(int row, int k, int kdim) { return (
 // out[0..M*N): D = A * B^T ; times[0] = round trip cycles, [1] = cycles per MMA back to back, [2] = ld x32 per warp, [3] = st x32
 __global__ void __launch_bounds__(128) tc2_kernel(const float* gA, const float* gB, float* out, long long* times, int variant) {
   __shared__ __align__(128) float sB[256 * K];  // first N*K used for numerics; the rest only for the N sweep
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar, bar2;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < N * K; i += blockDim.x) sB[i] = gB[i];
@@ -154,6 +154,24 @@ __global__ void __launch_bounds__(128) tc2_kernel(const float* gA, const float* 
   if (tid == 0) times[3] = (t1 - t0) / 64;
   if (acc == 0x12345678u) out[0] = 0.f;
 
+
+  // ---- several issuing threads: lane 0 of warps 0..NI-1 each issue 256 MMAs (N=32) into its own accumulator ----
+  for (int NI = 1; NI <= 4; NI *= 2) {
+    __syncthreads();
+    if (tid == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar2)), "r"(NI)); asm volatile("fence.mbarrier_init.release.cluster;"); }
+    __syncthreads();
+    t0 = clock64();
+    if ((tid & 31) == 0 && warp < NI) {
+      const uint64_t db = make_desc(smem_u32(sB), kstride, nstride);
+#pragma unroll 16
+      for (int i = 0; i < 256; ++i) mma_tf32_ts(tmem + 256 + 32 * warp, tmem + A_COL + (i & 3) * 8, db, idesc, 1);
+      commit(&bar2);
+    }
+    mbar_wait(&bar2, 0);
+    t1 = clock64();
+    if (tid == 0) times[9 + (NI == 1 ? 0 : NI == 2 ? 1 : 2)] = t1 - t0;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
@@ -184,6 +202,7 @@ int main() {
     printf("variant %d (%s): cuda=%s max_err=%g mismatches=%d/%d | cycles: round-trip(st,12 mma,ld)=%lld  per-mma=%lld  ld.x32=%lld  st.x32=%lld\n",
            variant, variant == 0 ? "field1=K stride, field2=N stride" : "swapped", cudaGetErrorString(e), maxerr, bad, M * N,
            t[0], t[1], t[2], t[3]);
+    printf("   N=32, 256 MMAs per issuing thread, total cycles: 1 issuer %lld  2 issuers %lld  4 issuers %lld\n", t[9], t[10], t[11]);
     printf("   256 back-to-back tf32 MMAs (M=128,K=8), cycles per MMA: N=16 %.1f  N=32 %.1f  N=64 %.1f  N=128 %.1f  N=256 %.1f\n",
            t[4] / 256.0, t[5] / 256.0, t[6] / 256.0, t[7] / 256.0, t[8] / 256.0);
     if (e != cudaSuccess) break;
