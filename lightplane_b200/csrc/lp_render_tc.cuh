@@ -530,27 +530,24 @@ LP_DEVICE void lp_gate_row(float (&x)[N], const unsigned char* tile, int chunk0,
 
 // leader: the group's parameter-gradient products over its 128 samples (8 k-steps of 16)
 template <int C>
-LP_DEVICE void lp_issue_dw(unsigned tmem, unsigned char* gs, int accumulate, int wi = 0, int nw = 1) {
+LP_DEVICE void lp_issue_dw(unsigned tmem, unsigned char* gs, int accumulate) {
   using B = BImg<C>;
   const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), a2 = lp_tc_mndesc_lo(gs + B::A2), dy = lp_tc_mndesc_lo(gs + B::DY),
                    dyl = lp_tc_mndesc_lo(gs + B::DYL);
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    if ((2 * ks) % nw == wi)
-      lp_tc_mma_ss_mn(tmem + BT_W, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 128, accumulate | (ks > 0));
-    if ((2 * ks + 1) % nw == wi)
-      lp_tc_mma_ss_mn(tmem + BT_L, lp_tc_kadv(a2, ks * 256), lp_tc_kadv(dyl, ks * 256), 2048, 16, accumulate | (ks > 0));
+    lp_tc_mma_ss_mn(tmem + BT_W, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 128, accumulate | (ks > 0));
+    lp_tc_mma_ss_mn(tmem + BT_L, lp_tc_kadv(a2, ks * 256), lp_tc_kadv(dyl, ks * 256), 2048, 16, accumulate | (ks > 0));
   }
 }
 // encoding^T x (step-sum of the colour-hidden gradient): A1 chunks 0-3 hold the encodings, DY chunks 8-11 the sums
 template <int C>
-LP_DEVICE void lp_issue_encw(unsigned tmem, unsigned char* gs, int accumulate, int wi = 0, int nw = 1) {
+LP_DEVICE void lp_issue_encw(unsigned tmem, unsigned char* gs, int accumulate) {
   using B = BImg<C>;
   const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), dy = lp_tc_mndesc_lo(gs + B::DY + 8 * 2048);
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks)
-    if (ks % nw == wi)
-      lp_tc_mma_ss_mn(tmem + BT_ENC, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 32, accumulate | (ks > 0));
+    lp_tc_mma_ss_mn(tmem + BT_ENC, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 32, accumulate | (ks > 0));
 }
 
 // adjoint of lp_gather_regs: the owner thread scatters its row into the grid gradient
