@@ -217,6 +217,19 @@ LP_DEVICE void lp_issue_layer(unsigned tbase, int d_col, int a_col, lp_kdesc_t w
   }
 }
 
+// Multi-issuer form used by the backward kernel: lane 0 of the group's warps 0..3 is issuer wi = 0..3 and
+// takes k-step wi of the product (three MMAs); every MMA accumulates, the epilogue threads having cleared
+// the accumulator (lp_tmem_zero) after reading the previous result, so the issue order is irrelevant.
+LP_DEVICE void lp_issue_layer_part(unsigned tbase, int d_col, int a_col, lp_kdesc_t whi, lp_kdesc_t wlo, int ksteps, int k0,
+                                   int nstride, int n, int lo_off, int wi) {
+  if (wi >= 0 && wi < ksteps) {
+    const lp_kdesc_t bh = lp_tc_kadv(whi, (k0 + wi) * 256), bl = lp_tc_kadv(wlo, (k0 + wi) * 256);
+    lp_tc_mma_ts(false, tbase + d_col, tbase + a_col + 8 * wi, bh, nstride, n, 1);
+    lp_tc_mma_ts(false, tbase + d_col, tbase + a_col + lo_off + 8 * wi, bh, nstride, n, 1);
+    lp_tc_mma_ts(false, tbase + d_col, tbase + a_col + 8 * wi, bl, nstride, n, 1);
+  }
+}
+
 // the owner thread samples all C channels of its sample point into registers
 // (CW channels starting at ch0: a sample's channels may be split over several threads)
 template <int C, int CW = C>
@@ -268,7 +281,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
   lp_build_img<C>(sm, params, D);
   if (tid == 0) {
-    for (int i = 0; i < ngroups; ++i) lp_mbar_init(bars + i, 1);
+    for (int i = 0; i < ngroups; ++i) lp_mbar_init(bars + i, 4);  // four issuing threads per group
     lp_mbar_init_fence();
   }
   if (tid < 32) lp_tmem_alloc512(tmem_slot);
@@ -278,7 +291,9 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
   lp_tc_fence_after();
   const unsigned tbase = *tmem_slot + (unsigned)(grp * TC_GROUP_COLS);
   const unsigned tme = lp_taddr(tbase, wig, 0);  // this thread's lane, column 0 of the group
-  const bool leader = (tid % GT) == 0;
+  const bool leader = (tid & 31) == 0;  // lane 0 of each of the group's four warps issues k-step `wig` (lp_issue_layer_part)
+  lp_tmem_zero<32>(tme + TC_D);
+  lp_tmem_zero<32>(tme + TC_D + 32);
   const float* F = reinterpret_cast<const float*>(sm + I::F32);
   const lp_kdesc_t w_t0h = lp_tc_kdesc_lo(sm + I::T0_HI), w_t0l = lp_tc_kdesc_lo(sm + I::T0_LO),
                    w_t1h = lp_tc_kdesc_lo(sm + I::T1_HI), w_t1l = lp_tc_kdesc_lo(sm + I::T1_LO),
@@ -320,13 +335,14 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
       lp_bar_sync(1 + grp, GT);
       if (leader) {
         lp_tc_fence_after();
-        lp_issue_layer(tbase, TC_D, TC_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, true);
+        lp_issue_layer_part(tbase, TC_D, TC_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, 16, wig);
         lp_tc_commit(bar);
       }
       float v[32];
       lp_mbar_wait(bar, phase); phase ^= 1;
       lp_tc_fence_after();
       lp_tmem_ld32u(tme + TC_D, v);
+      lp_tmem_zero<32>(tme + TC_D);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + j], 0.f);
       lp_stage_row<32>(tme + TC_A, v);
@@ -336,12 +352,13 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
       lp_bar_sync(1 + grp, GT);
       if (leader) {
         lp_tc_fence_after();
-        lp_issue_layer(tbase, TC_D, TC_A, w_t1h, w_t1l, 2, 0, 512, 32, true);
+        lp_issue_layer_part(tbase, TC_D, TC_A, w_t1h, w_t1l, 2, 0, 512, 32, 16, wig);
         lp_tc_commit(bar);
       }
       lp_mbar_wait(bar, phase); phase ^= 1;
       lp_tc_fence_after();
       lp_tmem_ld32u(tme + TC_D, v);
+      lp_tmem_zero<32>(tme + TC_D);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + 32 + j], 0.f);
       lp_stage_row<32>(tme + TC_A, v);
@@ -351,8 +368,8 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
       lp_bar_sync(1 + grp, GT);
       if (leader) {
         lp_tc_fence_after();
-        lp_issue_layer(tbase, TC_D, TC_A, w_och, w_ocl, 2, 0, 1024, 64, true);
-        lp_issue_layer(tbase, TC_D, TC_E, w_och, w_ocl, 2, 2, 1024, 64, false);
+        lp_issue_layer_part(tbase, TC_D, TC_A, w_och, w_ocl, 2, 0, 1024, 64, 16, wig);
+        lp_issue_layer_part(tbase, TC_D, TC_E, w_och, w_ocl, 2, 2, 1024, 64, 16, wig - 2);
         lp_tc_commit(bar);
       }
       lp_mbar_wait(bar, phase); phase ^= 1;
@@ -360,9 +377,11 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
       // ---- output layer (4 wide) on the CUDA cores, exact fp32 ----
       float raw = F[I::FBL + 3], lg0 = F[I::FBL], lg1 = F[I::FBL + 1], lg2 = F[I::FBL + 2];
       lp_tmem_ld32u(tme + TC_D, v);
+      lp_tmem_zero<32>(tme + TC_D);
 #pragma unroll
       for (int j = 0; j < 32; ++j) raw = fmaf(fmaxf(v[j] + F[I::FB + 64 + j], 0.f), F[I::FWO + j], raw);
       lp_tmem_ld32u(tme + TC_D + 32, v);
+      lp_tmem_zero<32>(tme + TC_D + 32);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float hc = fmaxf(v[j] + F[I::FB + 96 + j], 0.f);
@@ -403,6 +422,12 @@ static inline bool lp_tc_render_supported(const LpRenderArgs& a) {
   const LpLayer* ls[4] = {&D.trunk.l[0], &D.trunk.l[1], &D.opacity.l[0], &D.color.l[0]};
   for (int i = 0; i < 4; ++i)
     if (ls[i]->N != lptc::H) return false;
+  long long elems = 0;  // the kernels address the grid with 32-bit element offsets
+  for (int i = 0; i < a.G.n; ++i) {
+    const LpGrid& g = a.G.g[i];
+    elems = g.base + (long long)g.B * g.D * g.H * g.W * D.C;
+  }
+  if (elems >= (1ll << 31)) return false;
   return true;
 }
 
@@ -541,6 +566,29 @@ LP_DEVICE void lp_issue_dw(unsigned tmem, unsigned char* gs, int accumulate) {
   }
 }
 // encoding^T x (step-sum of the colour-hidden gradient): A1 chunks 0-3 hold the encodings, DY chunks 8-11 the sums
+// issuer wi of 4: k-steps 2wi, 2wi+1 of both products
+template <int C>
+LP_DEVICE void lp_issue_dw_part(unsigned tmem, unsigned char* gs, int wi) {
+  using B = BImg<C>;
+  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), a2 = lp_tc_mndesc_lo(gs + B::A2), dy = lp_tc_mndesc_lo(gs + B::DY),
+                   dyl = lp_tc_mndesc_lo(gs + B::DYL);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int ks = 2 * wi + j;
+    lp_tc_mma_ss_mn(tmem + BT_W, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 128, 1);
+    lp_tc_mma_ss_mn(tmem + BT_L, lp_tc_kadv(a2, ks * 256), lp_tc_kadv(dyl, ks * 256), 2048, 16, 1);
+  }
+}
+template <int C>
+LP_DEVICE void lp_issue_encw_part(unsigned tmem, unsigned char* gs, int wi) {
+  using B = BImg<C>;
+  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), dy = lp_tc_mndesc_lo(gs + B::DY + 8 * 2048);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int ks = 2 * wi + j;
+    lp_tc_mma_ss_mn(tmem + BT_ENC, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 32, 1);
+  }
+}
 template <int C>
 LP_DEVICE void lp_issue_encw(unsigned tmem, unsigned char* gs, int accumulate) {
   using B = BImg<C>;
@@ -579,6 +627,9 @@ LP_DEVICE void lp_splat_regs(const LpGridSet& G, float* grad, int b, float x, fl
   }
 }
 
+#ifndef LP_TC_ISSUERS
+#define LP_TC_ISSUERS 4  // MMA-issuing threads per group in the backward kernel (1 or 4)
+#endif
 #ifdef LP_ABL_NO_DW
 #define LP_ABL_DW(x)
 #else
@@ -611,7 +662,8 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
     *reinterpret_cast<unsigned short*>(gs + B::A2 + 8 * 2048 + (s >> 3) * 128 + (s & 7) * 16) = 0x3F80;
   }
   if (tid == 0) {
-    for (int i = 0; i < 9; ++i) lp_mbar_init(bars + i, 1);
+    for (int i = 0; i < 8; ++i) lp_mbar_init(bars + i, LP_TC_ISSUERS);
+    lp_mbar_init(bars + 8, 1);
     lp_mbar_init_fence();
   }
   if (tid < 32) lp_tmem_alloc512(tmem_slot);
@@ -631,10 +683,22 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
 
   const unsigned tbase = tmem + (unsigned)(grp * BT_GROUP_COLS);
   const unsigned tme = lp_taddr(tbase, wig, 0);
+#if LP_TC_ISSUERS == 4
+  const bool leader = lane == 0 && tg < 128;  // four issuing threads per group, see lp_issue_layer_part
+  const int wi = tg >> 5;
+#else
   const bool leader = tg == 0;
+#endif
   const float* F = reinterpret_cast<const float*>(sm + I::F32);
   float4* xch = reinterpret_cast<float4*>(gs + B::XCH);
   const int pk = (W / 2) * h, fc = W * h, ck = (W / 8) * h;  // packed-column / fp32-column / tile-chunk offset of this part
+#if LP_TC_ISSUERS == 4
+  lp_tmem_zero<W>(tme + BT_D + fc);
+  lp_tmem_zero<W>(tme + BT_D + 32 + fc);
+#define LP_TC_ZERO(n, addr) lp_tmem_zero<n>(addr)
+#else
+#define LP_TC_ZERO(n, addr)
+#endif
   const lp_kdesc_t w_t0h = lp_tc_kdesc_lo(sm + I::T0_HI), w_t0l = lp_tc_kdesc_lo(sm + I::T0_LO),
                    w_t1h = lp_tc_kdesc_lo(sm + I::T1_HI), w_t1l = lp_tc_kdesc_lo(sm + I::T1_LO),
                    w_och = lp_tc_kdesc_lo(sm + I::OC_HI), w_ocl = lp_tc_kdesc_lo(sm + I::OC_LO),
@@ -649,6 +713,15 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
   // A round trip to the tensor core is split in two so that independent work can run while the MMAs
   // execute: HANDOFF publishes this thread's staged operand row and lets the leader issue (ISSUE ends
   // with the commit to `bar`); WAIT blocks until the result is in tensor memory.
+#if LP_TC_ISSUERS == 4
+#define LP_ISSUE(A, WH, WL, KS, K0, NS, N, FIRST, LO, WI) lp_issue_layer_part(tbase, BT_D, A, WH, WL, KS, K0, NS, N, LO, WI)
+#define LP_ISSUE_DW() lp_issue_dw_part<C>(tmem, gs, wi)
+#define LP_ISSUE_ENCW() lp_issue_encw_part<C>(tmem, gs, wi)
+#else
+#define LP_ISSUE(A, WH, WL, KS, K0, NS, N, FIRST, LO, WI) lp_issue_layer(tbase, BT_D, A, WH, WL, KS, K0, NS, N, FIRST, LO)
+#define LP_ISSUE_DW() lp_issue_dw<C>(tmem, gs, 1)
+#define LP_ISSUE_ENCW() lp_issue_encw<C>(tmem, gs, 1)
+#endif
 #ifdef LP_ABL_NO_SYNC  // profiling only (results are garbage): no hand-off, no MMAs, no waits
 #define LP_TC_HANDOFF(ISSUE)
 #define LP_TC_WAIT()
@@ -721,25 +794,28 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
       lp_tile_row<CW>(gs + B::A1, 8 + (CW / 8) * h, s, x0);
       lp_stage_row<CW, 32>(tme + BT_A + (CW / 2) * h, x0);
       // ------------------------------ forward recompute ------------------------------
-      LP_TC_HANDOFF(lp_issue_layer(tbase, BT_D, BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, true, 32); lp_tc_commit(bar));
+      LP_TC_HANDOFF(LP_ISSUE(BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, true, 32, wi); lp_tc_commit(bar));
       if (have_prev && me.active && prev.oob != 0.f)
         lp_splat_regs<C, CW>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp, CW * h);
       LP_TC_WAIT();
       lp_tmem_ld<W>(tme + BT_D + fc, v);
+      LP_TC_ZERO(W, tme + BT_D + fc);
 #pragma unroll
       for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j] + F[I::FB + fc + j], 0.f);
       lp_tile_row<W>(gs + B::A1, 0 + ck, s, v);
       lp_stage_row<W, 32>(tme + BT_A + pk, v);
-      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_t1h, w_t1l, 2, 0, 512, 32, true, 32); lp_tc_commit(bar));
+      LP_TC_ROUND(LP_ISSUE(BT_A, w_t1h, w_t1l, 2, 0, 512, 32, true, 32, wi); lp_tc_commit(bar));
       lp_tmem_ld<W>(tme + BT_D + fc, v);
+      LP_TC_ZERO(W, tme + BT_D + fc);
 #pragma unroll
       for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j] + F[I::FB + 32 + fc + j], 0.f);
       lp_tile_row<W>(gs + B::A1, 4 + ck, s, v);
       lp_stage_row<W, 32>(tme + BT_A + pk, v);
-      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_och, w_ocl, 2, 0, 1024, 64, true, 32);
-                  lp_issue_layer(tbase, BT_D, BT_E, w_och, w_ocl, 2, 2, 1024, 64, false, 16); lp_tc_commit(bar));
+      LP_TC_ROUND(LP_ISSUE(BT_A, w_och, w_ocl, 2, 0, 1024, 64, true, 32, wi);
+                  LP_ISSUE(BT_E, w_och, w_ocl, 2, 2, 1024, 64, false, 16, wi - 2); lp_tc_commit(bar));
       float raw = 0.f, lg0 = 0.f, lg1 = 0.f, lg2 = 0.f;  // this part's share of the output layer
       lp_tmem_ld<W>(tme + BT_D + fc, v);
+      LP_TC_ZERO(W, tme + BT_D + fc);
 #pragma unroll
       for (int j = 0; j < W; ++j) {
         v[j] = fmaxf(v[j] + F[I::FB + 64 + fc + j], 0.f);
@@ -747,6 +823,7 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
       }
       lp_tile_row<W>(gs + B::A2, 0 + ck, s, v);
       lp_tmem_ld<W>(tme + BT_D + 32 + fc, v);
+      LP_TC_ZERO(W, tme + BT_D + 32 + fc);
 #pragma unroll
       for (int j = 0; j < W; ++j) {
         v[j] = fmaxf(v[j] + F[I::FB + 96 + fc + j], 0.f);
@@ -798,7 +875,7 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
       for (int j = 0; j < W; ++j) S[j] += v[j];
       lp_tile_row<W>(gs + B::DY, 8 + ck, s, v);
       lp_stage_row<W, 32>(tme + BT_A + 16 + pk, v);
-      LP_TC_HANDOFF(lp_issue_layer(tbase, BT_D, BT_A, w_xth, w_xtl, 4, 0, 1024, 32, true, 32); lp_tc_commit(bar));
+      LP_TC_HANDOFF(LP_ISSUE(BT_A, w_xth, w_xtl, 4, 0, 1024, 32, true, 32, wi); lp_tc_commit(bar));
       prev = cur;
       if (step + 1 < tot) {  // prefetch the next step's features while the product runs
         cur = sample_at(step + 1);
@@ -806,19 +883,22 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
       }
       LP_TC_WAIT();
       lp_tmem_ld<W>(tme + BT_D + fc, v);
+      LP_TC_ZERO(W, tme + BT_D + fc);
       lp_gate_row<W>(v, gs + B::A1, 4 + ck, s);  // d_t
       lp_tile_row<W>(gs + B::DY, 0 + ck, s, v);
       lp_stage_row<W, 32>(tme + BT_A + pk, v);
-      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_xhh, w_xhl, 2, 0, 512, 32, true, 32); lp_tc_commit(bar));
+      LP_TC_ROUND(LP_ISSUE(BT_A, w_xhh, w_xhl, 2, 0, 512, 32, true, 32, wi); lp_tc_commit(bar));
       lp_tmem_ld<W>(tme + BT_D + fc, v);
+      LP_TC_ZERO(W, tme + BT_D + fc);
       lp_gate_row<W>(v, gs + B::A1, 0 + ck, s);  // d_h1
       lp_tile_row<W>(gs + B::DY, 12 + ck, s, v);
       lp_stage_row<W, 32>(tme + BT_A + pk, v);
       lp_fence_async_smem();  // this step's tile writes -> visible to the tensor core
-      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A, w_x0h, w_x0l, 2, 0, 512, C, true, 32); lp_tc_commit(bar);
-                  LP_ABL_DW(lp_issue_dw<C>(tmem, gs, 1)); lp_tc_commit(bar_dw));
+      LP_TC_ROUND(LP_ISSUE(BT_A, w_x0h, w_x0l, 2, 0, 512, C, true, 32, wi); lp_tc_commit(bar);
+                  LP_ABL_DW(LP_ISSUE_DW()); lp_tc_commit(bar_dw));
       ++n_dw;
       lp_tmem_ld<CW>(tme + BT_D + CW * h, dxp);
+      LP_TC_ZERO(CW, tme + BT_D + CW * h);
 #pragma unroll
       for (int c = 0; c < CW; ++c) dxp[c] *= prev.oob;
       have_prev = true;
@@ -842,10 +922,11 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
       lp_stage_row<W, 32>(tme + BT_A + 16 + pk, S);  // K index 32..63 of the d_t weight tile = colour hidden
       lp_fence_async_smem();
       float v[W];
-      LP_TC_ROUND(lp_issue_layer(tbase, BT_D, BT_A + 16, w_xth, w_xtl, 2, 2, 1024, 32, true, 32); lp_tc_commit(bar);
-                  lp_issue_encw<C>(tmem, gs, 1); lp_tc_commit(bar_dw));
+      LP_TC_ROUND(LP_ISSUE(BT_A + 16, w_xth, w_xtl, 2, 2, 1024, 32, true, 32, wi); lp_tc_commit(bar);
+                  LP_ISSUE_ENCW(); lp_tc_commit(bar_dw));
       ++n_dw;
       lp_tmem_ld<W>(tme + BT_D + fc, v);
+      LP_TC_ZERO(W, tme + BT_D + fc);
       if (me.active) {
         float4* ge = reinterpret_cast<float4*>(io.g_enc + (long long)me.ray * H + fc);
 #pragma unroll
@@ -856,6 +937,10 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
 #undef LP_TC_ROUND
 #undef LP_TC_HANDOFF
 #undef LP_TC_WAIT
+#undef LP_ISSUE
+#undef LP_ISSUE_DW
+#undef LP_ISSUE_ENCW
+#undef LP_TC_ZERO
   // ---- drain, then the CTA's first four warps read the accumulators (TMEM lane = stack row) ----
 #ifndef LP_ABL_NO_SYNC
   if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
