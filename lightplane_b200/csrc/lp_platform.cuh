@@ -124,6 +124,9 @@ LP_DEVICE unsigned lp_tc_kdesc_lo(const void* smem_ptr) { return ((lp_smem_u32(s
 typedef unsigned lp_kdesc_t;
 LP_DEVICE lp_kdesc_t lp_tc_kadv(lp_kdesc_t lo, int bytes) { return lo + (unsigned)(bytes >> 4); }
 LP_DEVICE void lp_tc_mma_ts(bool tf32, unsigned d_taddr, unsigned a_taddr, unsigned b_lo, int nstride, int n, int accumulate) {
+#ifdef LP_ABL_NO_MMA  // profiling only: hand-offs and waits stay, the tensor core does nothing
+  return;
+#endif
   const unsigned fmt = tf32 ? 2u : 1u;
   const unsigned idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(n >> 3) << 17) | (8u << 24);
   const unsigned hi = (unsigned)(nstride >> 4) | (1u << 14);
@@ -140,6 +143,9 @@ LP_DEVICE void lp_tc_mma_ts(bool tf32, unsigned d_taddr, unsigned a_taddr, unsig
 // element (mn, k) at (mn/8)*sbo + (k/8)*128 + (k%8)*16 + (mn%8)*2.  D(128 x n) (+)= A(128 x 16) * B(16 x n).
 LP_DEVICE lp_kdesc_t lp_tc_mndesc_lo(const void* smem_ptr) { return ((lp_smem_u32(smem_ptr) >> 4) & 0x3FFF) | (8u << 16); }
 LP_DEVICE void lp_tc_mma_ss_mn(unsigned d_taddr, lp_kdesc_t a_lo, lp_kdesc_t b_lo, int sbo, int n, int accumulate) {
+#ifdef LP_ABL_NO_MMA
+  return;
+#endif
   const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(n >> 3) << 17) | (8u << 24);
   const unsigned hi = (unsigned)(sbo >> 4) | (1u << 14);
   asm volatile(
