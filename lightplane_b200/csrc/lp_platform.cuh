@@ -233,5 +233,12 @@ LP_DEVICE void lp_tmem_ld(unsigned taddr, float (&v)[N]) {
 }
 // named barrier over `nthreads` threads (ids 1..15; 0 is __syncthreads)
 LP_DEVICE void lp_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// named barrier with an OR reduction: true iff `pred` holds for any of the `nthreads` threads
+LP_DEVICE bool lp_bar_any(int id, int nthreads, bool pred) {
+  unsigned r;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.red.or.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(r) : "r"(id), "r"(nthreads), "r"((unsigned)pred) : "memory");
+  return r != 0;
+}
 #endif  // !LP_HOSTSIM
 

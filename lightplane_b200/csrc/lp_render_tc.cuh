@@ -1,5 +1,5 @@
 // Renderer fast path for the default decoder shape (trunk/opacity/colour = 2/2/2 layers, hidden width
-// 32, C in {16,32} grid channels, <= 3 colour channels, no colour grid / scaffold): the per-sample MLP
+// 32, C in {16,32} grid channels, <= 3 colour channels, no separate colour grid): the per-sample MLP
 // runs on the 5th-generation tensor cores (tcgen05) with one THREAD per sample.  Other decoder shapes
 // take the generic kernels of lp_render_generic.cuh.
 //
@@ -268,8 +268,9 @@ LP_DEVICE void lp_gather_regs(const LpGridSet& G, int b, float x, float y, float
 // ===========================================================================================
 // forward
 // ===========================================================================================
-template <int C>
+template <int C, bool SCAF>
 __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
+                                                                   LpGridSet SC,
                                                                    const float* __restrict__ params,
                                                                    float* __restrict__ out_len, float* __restrict__ out_nlt,
                                                                    float* __restrict__ out_feat, int feat_stride) {
@@ -321,9 +322,14 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
       const Sched sc = lp_sched(step, M);
       float depth, delta;
       lp_depth_delta(sc, me.near, me.far, depth, delta);
+      float occ = 1.f;
       {
         float x = me.ox + depth * me.dx, y = me.oy + depth * me.dy, z = me.oz + depth * me.dz;
         if (M.contract) lp_contract(x, y, z);
+        if (SCAF) {  // occupancy scaffold (renderer_fw.py:234-252): a step whose 128 samples are all in
+          occ = lp_nearest(SC, me.b, x, y, z);  // empty space changes nothing and is skipped by the whole group
+          if (!lp_bar_any(1 + grp, GT, occ != 0.f)) continue;
+        }
         const float oob = M.mask_oob ? lp_in_bounds(x, y, z) : 1.f;
         float x0[C];
         lp_gather_regs<C>(G, me.b, x, y, z, oob, x0);
@@ -390,14 +396,15 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
       }
       // ---- compositing (renderer_fw.py:289-340) ----
       if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-      nlt += delta * M.gain * lp_softplus(raw);
+      nlt += SCAF ? delta * M.gain * lp_softplus(raw) * occ : delta * M.gain * lp_softplus(raw);
       const float Tn = expf(-nlt);
       const float w = T - Tn;
       T = Tn;
       acc_len = fmaf(w, depth, acc_len);
-      acc_c[0] = fmaf(w, lp_sigmoid(lg0), acc_c[0]);
-      acc_c[1] = fmaf(w, lp_sigmoid(lg1), acc_c[1]);
-      acc_c[2] = fmaf(w, lp_sigmoid(lg2), acc_c[2]);
+      const float wc = SCAF ? w * occ : w;
+      acc_c[0] = fmaf(wc, lp_sigmoid(lg0), acc_c[0]);
+      acc_c[1] = fmaf(wc, lp_sigmoid(lg1), acc_c[1]);
+      acc_c[2] = fmaf(wc, lp_sigmoid(lg2), acc_c[2]);
     }
     if (me.active) {
       out_len[me.ray] = acc_len;
@@ -415,7 +422,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
 // -------------------------------------------------------------------------------------------
 static inline bool lp_tc_render_supported(const LpRenderArgs& a) {
   const LpDecoder& D = a.D;
-  if (D.use_color_grid || a.use_scaffold) return false;
+  if (D.use_color_grid) return false;
   if (D.trunk.n_layers != 2 || D.opacity.n_layers != 2 || D.color.n_layers != 2) return false;
   if (D.C != 16 && D.C != 32) return false;
   if (D.n_feat > 3 || D.in_c != lptc::H) return false;
@@ -444,24 +451,27 @@ static inline int lp_tc_num_sms() {
 }
 #endif
 
-template <int C>
+template <int C, bool SCAF>
 static int lp_tc_render_forward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, float* out_len, float* out_nlt,
                                   float* out_feat, int feat_stride) {
   const int groups = 4;
   const size_t bytes = Img<C>::FWD_END + 128;
-  if (LP_TC_SET_SMEM(lp_render_fwd_tc_kernel<C>, bytes)) return LP_ERR_CUDA;
+  if (LP_TC_SET_SMEM((lp_render_fwd_tc_kernel<C, SCAF>), bytes)) return LP_ERR_CUDA;
   const int tiles = (a.R.n + GT - 1) / GT;
   int blocks = (tiles + groups - 1) / groups;
   const int max_blocks = lp_tc_num_sms();  // persistent; one CTA per SM owns its tensor memory
   if (blocks > max_blocks) blocks = max_blocks;
-  LP_LAUNCH(lp_render_fwd_tc_kernel<C>, dim3(blocks), dim3(groups * GT), bytes, st, a.R, a.M, a.D, a.G, params, out_len,
+  LP_LAUNCH((lp_render_fwd_tc_kernel<C, SCAF>), dim3(blocks), dim3(groups * GT), bytes, st, a.R, a.M, a.D, a.G, a.SC, params, out_len,
             out_nlt, out_feat, feat_stride);
   return LP_OK;
 }
 static inline int lp_tc_render_forward(cudaStream_t st, const LpRenderArgs& a, const float* params, float* out_len,
                                        float* out_nlt, float* out_feat, int feat_stride) {
-  if (a.D.C == 16) return lp_tc_render_forward_t<16>(st, a, params, out_len, out_nlt, out_feat, feat_stride);
-  return lp_tc_render_forward_t<32>(st, a, params, out_len, out_nlt, out_feat, feat_stride);
+  if (a.use_scaffold)
+    return a.D.C == 16 ? lp_tc_render_forward_t<16, true>(st, a, params, out_len, out_nlt, out_feat, feat_stride)
+                       : lp_tc_render_forward_t<32, true>(st, a, params, out_len, out_nlt, out_feat, feat_stride);
+  return a.D.C == 16 ? lp_tc_render_forward_t<16, false>(st, a, params, out_len, out_nlt, out_feat, feat_stride)
+                     : lp_tc_render_forward_t<32, false>(st, a, params, out_len, out_nlt, out_feat, feat_stride);
 }
 
 
@@ -640,8 +650,9 @@ LP_DEVICE void lp_splat_regs(const LpGridSet& G, float* grad, int b, float x, fl
 // parts address the same TMEM lane (warps w and w+4 of a group share a lane quarter).  NP = 2 halves the
 // per-thread work and registers, doubling the warps that hide the tensor-core round trips, at the
 // price of duplicated ray/tap/compositing arithmetic and one exchange of the output layer's partial sums.
-template <int C, int NP>
+template <int C, int NP, bool SCAF>
 __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
+                                                                        LpGridSet SC,
                                                                         const float* __restrict__ params, LpBwdIo io) {
   using I = Img<C>;
   using B = BImg<C>;
@@ -770,7 +781,7 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
     // Software pipeline across steps: the gather of step n+1 is issued while the tensor core runs the
     // first input-gradient product of step n, and the scatter of step n while it runs the first layer
     // of step n+1 -- the two memory-bound, MMA-independent pieces hide inside the waits.
-    struct Pos { float depth, delta, x, y, z, oob; };
+    struct Pos { float depth, delta, x, y, z, oob, occ; };
     auto sample_at = [&](int step) {
       Pos p;
       const Sched sc = lp_sched(step, M);
@@ -778,6 +789,7 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
       p.x = me.ox + p.depth * me.dx; p.y = me.oy + p.depth * me.dy; p.z = me.oz + p.depth * me.dz;
       if (M.contract) lp_contract(p.x, p.y, p.z);
       p.oob = M.mask_oob ? lp_in_bounds(p.x, p.y, p.z) : 1.f;
+      p.occ = SCAF ? lp_nearest(SC, me.b, p.x, p.y, p.z) : 1.f;
       return p;
     };
     Pos cur = sample_at(0), prev = cur;
@@ -787,6 +799,15 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
 
     for (int step = 0; step < tot; ++step) {
       float v[W];
+      // occupancy scaffold (renderer_bw.py, as renderer_fw.py:234-252): a step whose 128 samples are all in empty
+      // space has zero weight and zero gradient and is skipped by the whole group (the pipeline just advances)
+      if (SCAF && !lp_bar_any(1 + grp, GTH, cur.occ != 0.f)) {
+        if (step + 1 < tot) {
+          cur = sample_at(step + 1);
+          lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
+        }
+        continue;
+      }
       // the previous step's parameter-gradient products must have consumed the tiles
 #ifndef LP_ABL_NO_SYNC
       if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
@@ -844,19 +865,21 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
       float g_raw, dl0, dl1, dl2;
       {
         if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-        nlt += cur.delta * M.gain * lp_softplus(raw);
+        const float occ = SCAF ? cur.occ : 1.f;  // compile-time 1 without a scaffold
+        nlt += cur.delta * M.gain * lp_softplus(raw) * occ;
         const float Tn = expf(-nlt);
         const float w = T - Tn;
         T = Tn;
         const float s0 = lp_sigmoid(lg0), s1 = lp_sigmoid(lg1), s2 = lp_sigmoid(lg2);
-        const float p = fmaf(cur.depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2])));
+        const float p = fmaf(cur.depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2]))) * occ;
         prefix = fmaf(w, p, prefix);
         const float suffix = (step == tot - 1) ? 0.f : total - prefix;
         const float g_dop = Tn * p - suffix + g_nlt;
-        g_raw = g_dop * cur.delta * M.gain * lp_sigmoid(raw);
-        dl0 = w * gF[0] * s0 * (1.f - s0);
-        dl1 = w * gF[1] * s1 * (1.f - s1);
-        dl2 = w * gF[2] * s2 * (1.f - s2);
+        g_raw = g_dop * cur.delta * M.gain * occ * lp_sigmoid(raw);
+        const float wo = w * occ;
+        dl0 = wo * gF[0] * s0 * (1.f - s0);
+        dl1 = wo * gF[1] * s1 * (1.f - s1);
+        dl2 = wo * gF[2] * s2 * (1.f - s2);
       }
       if (h == 0) lp_tile8(gs + B::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
       // ------------------------------ backward sweep ------------------------------
@@ -1000,22 +1023,23 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
 #ifndef LP_TC_BWD_NP
 #define LP_TC_BWD_NP 2  // threads per sample in the backward kernel
 #endif
-template <int C>
+template <int C, bool SCAF>
 static int lp_tc_render_backward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
   const int groups = 2;
   constexpr int NP = LP_TC_BWD_NP;
   const size_t bytes = BImg<C>::GROUPS + (size_t)groups * BImg<C>::GROUP_BYTES;
-  if (LP_TC_SET_SMEM((lp_render_bwd_tc_kernel<C, NP>), bytes)) return LP_ERR_CUDA;
+  if (LP_TC_SET_SMEM((lp_render_bwd_tc_kernel<C, NP, SCAF>), bytes)) return LP_ERR_CUDA;
   const int tiles = (a.R.n + GT - 1) / GT;
   int blocks = (tiles + groups - 1) / groups;
   const int max_blocks = lp_tc_num_sms();
   if (blocks > max_blocks) blocks = max_blocks;
-  LP_LAUNCH((lp_render_bwd_tc_kernel<C, NP>), dim3(blocks), dim3(groups * GT * NP), bytes, st, a.R, a.M, a.D, a.G, params, io);
+  LP_LAUNCH((lp_render_bwd_tc_kernel<C, NP, SCAF>), dim3(blocks), dim3(groups * GT * NP), bytes, st, a.R, a.M, a.D, a.G, a.SC, params, io);
   return LP_OK;
 }
 static inline int lp_tc_render_backward(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
-  if (a.D.C == 16) return lp_tc_render_backward_t<16>(st, a, params, io);
-  return lp_tc_render_backward_t<32>(st, a, params, io);
+  if (a.use_scaffold)
+    return a.D.C == 16 ? lp_tc_render_backward_t<16, true>(st, a, params, io) : lp_tc_render_backward_t<32, true>(st, a, params, io);
+  return a.D.C == 16 ? lp_tc_render_backward_t<16, false>(st, a, params, io) : lp_tc_render_backward_t<32, false>(st, a, params, io);
 }
 
 }  // namespace lptc

@@ -112,7 +112,7 @@ def oracle_splat_case(c, dtype=torch.float64):
     return {k: v.detach() for k, v in res.items()}
 
 
-def coherent_case(c, n=64, pixel=0.02, seed=5, batch_blocks=True, mask_oob=None, plane=None):
+def coherent_case(c, n=64, pixel=0.02, seed=5, batch_blocks=True, mask_oob=None, plane=None, scaffold_res=None):
     """A copy of golden case `c` whose rays are replaced by `n` neighbouring pixels of a pinhole camera
     (the layout real renders have, and the one the backward kernel's warp-level scatter aggregation is
     built for); expected values then come from the oracle.  `plane`: optionally resize every grid to
@@ -142,4 +142,11 @@ def coherent_case(c, n=64, pixel=0.02, seed=5, batch_blocks=True, mask_oob=None,
         c["grid_sizes"] = sizes
         rows = int(sum(int(np.prod(s[:4])) for s in sizes))
         c["grid"] = torch.randn(rows, int(sizes[0][4]), generator=g)
+    if scaffold_res is not None:  # occupancy scaffold: a ball around the origin plus a few random cells, so that the
+        r = scaffold_res            # first and last samples of every ray are in empty space (whole-group skips)
+        ax = (torch.arange(r).float() + 0.5) / r * 2 - 1
+        zz, yy, xx = torch.meshgrid(ax, ax, ax, indexing="ij")
+        ball = ((xx ** 2 + yy ** 2 + zz ** 2) < 0.45).float()
+        B = int(c["grid_sizes"][0][0])
+        c["scaffold"] = torch.stack([torch.maximum(ball, (torch.rand(r, r, r, generator=g) > 0.97).float()) for _ in range(B)])
     return c

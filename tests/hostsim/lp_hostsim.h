@@ -66,6 +66,7 @@ struct BlockCtx {
   float* tmem;  // emulated tensor memory: [128 lanes][512 columns]
   std::mutex named_mu;
   std::unique_ptr<std::barrier<>> named[16];
+  std::atomic<int> red[16][3];
 };
 
 struct ThreadCtx {
@@ -99,6 +100,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
         std::vector<float> tmem(128 * 512, 0.f);
         BlockCtx bctx;
         bctx.bar = &block_bar; bctx.smem = smem_aligned; bctx.warps = &warps; bctx.tmem = tmem.data();
+        for (auto& r : bctx.red) { r[0] = 0; r[1] = 0; r[2] = 0; }
         std::vector<std::thread> threads;
         threads.reserve(nthreads);
         for (unsigned t = 0; t < nthreads; ++t) {
@@ -329,6 +331,15 @@ static inline void lp_bar_sync(int id, int nthreads) {
     bar = b->named[id].get();
   }
   bar->arrive_and_wait();
+}
+static inline bool lp_bar_any(int id, int nthreads, bool pred) {
+  static thread_local unsigned gen[16] = {0};
+  auto* b = lp_hostsim::g_ctx->block;
+  const int slot = (int)(gen[id]++ % 3u);
+  b->red[id][(slot + 1) % 3].store(0);  // next vote's slot: last read two votes ago, i.e. before the previous barrier
+  if (pred) b->red[id][slot].fetch_or(1);
+  lp_bar_sync(id, nthreads);
+  return b->red[id][slot].load() != 0;
 }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
   unsigned long long v = ((unsigned long long)y << 32) | x;

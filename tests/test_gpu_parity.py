@@ -50,15 +50,25 @@ def test_renderer_cabi_vs_golden(lib, name):
     ("render_triplane_inf_gain", 400, 0.05, 64, 0),     # wide footprints
     ("render_c32_b1", 576, 0.003, 48, 1),               # 32 channels
 ])
-def test_renderer_coherent_rays_vs_oracle(lib, name, n, pixel, plane, mask):
+def test_renderer_coherent_rays_vs_oracle(lib, name, n, pixel, plane, mask, scaf=None):
     """Camera-like neighbouring rays (what a render looks like, unlike the golden cases' random rays):
     overlapping footprints contend on the same texels and many samples miss the planes."""
-    c = coherent_case(load_case(name), n=n, pixel=pixel, mask_oob=mask, plane=plane)
+    c = coherent_case(load_case(name), n=n, pixel=pixel, mask_oob=mask, plane=plane, scaffold_res=scaf)
     want = oracle_render_case(c)
     got = render_case(lib, c, "cuda")
     for k, v in got.items():
         tol = TOL_GMLP_TINY if k == "g_mlp" else (TOL_GRAD if k.startswith("g_") else TOL)
         assert rel_err(v, want[k]) < tol, (name, k, rel_err(v, want[k]))
+
+
+@pytest.mark.parametrize("name,n,pixel,plane,mask,scaf", [
+    ("render_triplane_inf_gain", 1024, 0.002, 64, 0, 16),
+    ("render_c32_b1", 576, 0.003, 48, 1, 12),
+])
+def test_renderer_scaffold_tensor_core_path(lib, name, n, pixel, plane, mask, scaf):
+    """Occupancy scaffold on the tensor-core path: per-sample occupancy factors and whole-group skips of steps
+    whose 128 samples are all in empty space (renderer_fw.py:234-252)."""
+    test_renderer_coherent_rays_vs_oracle(lib, name, n, pixel, plane, mask, scaf)
 
 
 @pytest.mark.parametrize("name", case_names("splat_"))

@@ -44,12 +44,13 @@ def test_hostsim_splatter(lib, name):
         assert rel_err(v, c["naive_" + k]) < 2e-4, (name, k, rel_err(v, c["naive_" + k]))
 
 
-@pytest.mark.parametrize("name,pixel,mask", [("render_triplane_inf_gain", 0.02, 0), ("render_triplane_inf_gain", 0.08, 1),
-                                             ("render_c32_b1", 0.03, 1)])
-def test_hostsim_renderer_coherent_rays(lib, name, pixel, mask):
+@pytest.mark.parametrize("name,pixel,mask,scaf", [("render_triplane_inf_gain", 0.02, 0, None), ("render_triplane_inf_gain", 0.08, 1, None),
+                                                  ("render_c32_b1", 0.03, 1, None), ("render_triplane_inf_gain", 0.02, 0, 8),
+                                                  ("render_c32_b1", 0.03, 1, 6)])
+def test_hostsim_renderer_coherent_rays(lib, name, pixel, mask, scaf):
     """Neighbouring-pixel rays (overlapping footprints, many samples outside the planes), unlike the
     golden cases' random rays."""
-    c = coherent_case(load_case(name), n=64, pixel=pixel, mask_oob=mask)
+    c = coherent_case(load_case(name), n=64, pixel=pixel, mask_oob=mask, scaffold_res=scaf)
     want = oracle_render_case(c)
     got = render_case(lib, c, "cpu")
     for k, v in got.items():
