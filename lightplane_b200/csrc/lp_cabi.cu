@@ -8,6 +8,7 @@
 #include "lp_render_generic.cuh"
 #include "lp_splat.cuh"
 #include "lp_render_tc.cuh"
+#include "lp_render_tc_cg.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -232,6 +233,12 @@ int lp_render_forward(void* stream, const lp_march_cfg* cfg, const lp_decoder_sp
       LP_FAIL(rc, "fast forward launch setup failed");
     return lp_check_launch("lp_render_forward(fast)");
   }
+  if (lptc::lp_cg_render_supported(a)) {
+    if ((rc = lptc::lp_cg_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance, out_features,
+                                         features_stride)))
+      LP_FAIL(rc, "colour-grid forward launch setup failed");
+    return lp_check_launch("lp_render_forward(colour grid)");
+  }
   const int pf = (a.D.n_params + 3) & ~3;
   const int per_warp = (a.A.total + a.D.in_c + a.D.n_feat) * LP_LS;
   int warps, pin; size_t bytes;
@@ -271,6 +278,10 @@ int lp_render_backward(void* stream, const lp_march_cfg* cfg, const lp_decoder_s
   if (lptc::lp_tc_render_supported(a)) {
     if ((rc = lptc::lp_tc_render_backward(st, a, mlp_params, io))) LP_FAIL(rc, "fast backward launch setup failed");
     return lp_check_launch("lp_render_backward(fast)");
+  }
+  if (lptc::lp_cg_render_supported(a)) {
+    if ((rc = lptc::lp_cg_render_backward(st, a, mlp_params, io))) LP_FAIL(rc, "colour-grid backward launch setup failed");
+    return lp_check_launch("lp_render_backward(colour grid)");
   }
   const int pf = (a.D.n_params + 3) & ~3;
   const int per_warp = (a.A.total + 3 * a.D.max_dim + 2 * a.D.in_c + a.D.n_feat) * LP_LS;

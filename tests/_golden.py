@@ -150,3 +150,29 @@ def coherent_case(c, n=64, pixel=0.02, seed=5, batch_blocks=True, mask_oob=None,
         B = int(c["grid_sizes"][0][0])
         c["scaffold"] = torch.stack([torch.maximum(ball, (torch.rand(r, r, r, generator=g) > 0.97).float()) for _ in range(B)])
     return c
+
+
+def synthetic_case(n=96, C=16, hidden=32, layers=(0, 2, 2), color_grid=True, plane=6, batch=2, samples=6, samples_inf=2,
+                   mask_oob=1, contract=0, sigma=0.0, seed=3, pixel=0.03):
+    """A renderer case built from scratch (decoder from `init_decoder_params`, camera-like rays) in the dict layout
+    of the golden files, for configurations the golden set lacks; expected values come from the oracle."""
+    import lightplane_b200 as lp
+
+    g = torch.Generator().manual_seed(seed)
+    nt, no, nc = layers
+    torch.manual_seed(seed)
+    dp = lp.init_decoder_params("cpu", no, nt, nc, input_chn=C, hidden_chn=hidden, color_chn=3, opacity_init_bias=-1.0,
+                                use_separate_color_grid=color_grid)
+    sizes = np.array([[batch, 1, plane, plane + 1, C], [batch, plane - 1, 1, plane + 1, C], [batch, plane - 1, plane, 1, C]])
+    rows = int(sum(int(np.prod(s[:4])) for s in sizes))
+    c = dict(
+        grid=torch.randn(rows, C, generator=g), grid_sizes=sizes,
+        mlp_params=dp.mlp_params.detach() + 0.05 * torch.randn(dp.mlp_params.shape, generator=g),
+        n_hidden_trunk=dp.n_hidden_trunk.numpy(), n_hidden_opacity=dp.n_hidden_opacity.numpy(),
+        n_hidden_color=dp.n_hidden_color.numpy(), color_chn=np.int32(3),
+        cfg=np.array([samples, samples_inf, mask_oob, contract, 11]), cfg_f=np.array([1.5, 1e-5, sigma]),
+        encoding=torch.zeros(n, C if color_grid else hidden), cot_features=torch.zeros(n, 3),
+    )
+    if color_grid:
+        c["color_grid"] = torch.randn(rows, C, generator=g)
+    return coherent_case(c, n=n, pixel=pixel, seed=seed)

@@ -6,7 +6,7 @@ to 2e-4 (mean|d|/mean|ref|)."""
 import pytest
 import torch
 
-from _golden import (case_names, coherent_case, load_case, oracle_render_case, oracle_splat_case, rel_err,
+from _golden import (case_names, coherent_case, load_case, synthetic_case, oracle_render_case, oracle_splat_case, rel_err,
                      renderer_cfg, splat_cfg)
 from _lowlevel import render_case, splat_case
 
@@ -69,6 +69,17 @@ def test_renderer_scaffold_tensor_core_path(lib, name, n, pixel, plane, mask, sc
     """Occupancy scaffold on the tensor-core path: per-sample occupancy factors and whole-group skips of steps
     whose 128 samples are all in empty space (renderer_fw.py:234-252)."""
     test_renderer_coherent_rays_vs_oracle(lib, name, n, pixel, plane, mask, scaf)
+
+
+@pytest.mark.parametrize("C,n,plane,sigma", [(16, 2048, 48, 0.0), (32, 777, 40, 0.5)])
+def test_renderer_color_grid_tensor_core_path(lib, C, n, plane, sigma):
+    """Separate colour grid ("ReLU field", trunk-less decoder, hidden 32) on its tensor-core path."""
+    c = synthetic_case(n=n, C=C, plane=plane, samples=24, samples_inf=3, sigma=sigma, pixel=0.004, batch=1)
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cuda")
+    for k, v in got.items():
+        tol = TOL_GMLP_TINY if k == "g_mlp" else (TOL_GRAD if k.startswith("g_") else TOL)
+        assert rel_err(v, want[k]) < tol, (C, k, rel_err(v, want[k]))
 
 
 @pytest.mark.parametrize("name", case_names("splat_"))

@@ -7,7 +7,7 @@ import subprocess
 import pytest
 import torch
 
-from _golden import case_names, coherent_case, load_case, oracle_render_case, rel_err
+from _golden import case_names, coherent_case, load_case, oracle_render_case, rel_err, synthetic_case
 from _lowlevel import render_case, splat_case
 from lightplane_b200 import _cabi
 
@@ -56,3 +56,14 @@ def test_hostsim_renderer_coherent_rays(lib, name, pixel, mask, scaf):
     for k, v in got.items():
         tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
         assert rel_err(v, want[k]) < tol, (name, k, rel_err(v, want[k]))
+
+
+@pytest.mark.parametrize("C,sigma", [(16, 0.0), (32, 0.5)])
+def test_hostsim_renderer_color_grid_tensor_core_path(lib, C, sigma):
+    """Separate colour grid ("ReLU field", trunk-less decoder, hidden 32): lp_render_tc_cg.cuh."""
+    c = synthetic_case(n=96, C=C, sigma=sigma)
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cpu")
+    for k, v in got.items():
+        tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
+        assert rel_err(v, want[k]) < tol, (C, k, rel_err(v, want[k]))
