@@ -9,6 +9,7 @@
 #include "lp_splat.cuh"
 #include "lp_render_tc.cuh"
 #include "lp_render_tc_cg.cuh"
+#include "lp_splat_tc.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -408,6 +409,11 @@ int lp_mlp_splat_forward(void* stream, const lp_march_cfg* cfg, const lp_mlp_spe
   if ((rc = lp_make_rays(rays, &R, IN.C))) return rc;
   if (IN.g[0].B != O.g[0].B) LP_FAIL(LP_ERR_INVALID_ARG, "input / output grid batch sizes differ");
   if (R.n == 0) return LP_OK;
+  if (lptc::lp_tc_mlp_splat_supported(S, IN, O)) {
+    if ((rc = lptc::lp_tc_mlp_splat_forward((cudaStream_t)stream, R, M, S, IN, O, weight_grid, valid_mask, mlp_params)))
+      LP_FAIL(rc, "tensor-core MLP splatter launch setup failed");
+    return lp_check_launch("lp_mlp_splat_forward(tc)");
+  }
   const int pf = (S.n_params + 3) & ~3;
   const int per_warp = (S.total + S.c_in + S.c_out) * LP_LS;
   int warps, pin; size_t bytes;
@@ -433,6 +439,12 @@ int lp_mlp_splat_backward(void* stream, const lp_march_cfg* cfg, const lp_mlp_sp
   if ((rc = lp_make_splat_mlp(spec, IN.C, GG.C, &S))) return rc;
   if ((rc = lp_make_rays(rays, &R, IN.C))) return rc;
   if (R.n == 0) return LP_OK;
+  if (lptc::lp_tc_mlp_splat_supported(S, IN, GG)) {
+    if ((rc = lptc::lp_tc_mlp_splat_backward((cudaStream_t)stream, R, M, S, IN, GG, valid_mask, mlp_params, grad_feature,
+                                             grad_mlp_params, grad_input_grid)))
+      LP_FAIL(rc, "tensor-core MLP splatter launch setup failed");
+    return lp_check_launch("lp_mlp_splat_backward(tc)");
+  }
   const int pf = (S.n_params + 3) & ~3;
   const int per_warp = (S.total + 2 * S.max_dim + 2 * S.c_in) * LP_LS;
   int warps, pin; size_t bytes;

@@ -176,3 +176,34 @@ def synthetic_case(n=96, C=16, hidden=32, layers=(0, 2, 2), color_grid=True, pla
     if color_grid:
         c["color_grid"] = torch.randn(rows, C, generator=g)
     return coherent_case(c, n=n, pixel=pixel, seed=seed)
+
+
+def synthetic_splat_case(n=96, c_in=16, c_out=16, hidden=32, layers=2, res=6, batch=2, samples=6, samples_inf=2,
+                         mask_oob=1, contract=0, seed=4, pixel=0.03, triplane=False):
+    """An MLP-splatter case built from scratch in the dict layout of the golden files."""
+    import lightplane_b200 as lp
+
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    sp = lp.init_splatter_params("cpu", n_layers=layers, input_chn=c_in, hidden_chn=hidden, out_chn=c_out)
+
+    def shapes(C):
+        if triplane:
+            return np.array([[batch, 1, res, res + 1, C], [batch, res - 1, 1, res + 1, C], [batch, res - 1, res, 1, C]])
+        return np.array([[batch, res - 1, res, res + 1, C]])
+
+    out_sizes, in_sizes = shapes(c_out), shapes(c_in)
+    rows = lambda sz: int(sum(int(np.prod(q[:4])) for q in sz))
+    w = int(n ** 0.5)
+    ii = torch.arange(n)
+    px, py = (ii % w).float() - w / 2, (ii // w).float() - w / 2
+    d = torch.stack([px * pixel + 0.03, py * pixel - 0.02, torch.ones(n)], -1)
+    return dict(
+        directions=d / d.norm(dim=-1, keepdim=True), origins=torch.tensor([0.1, -0.15, -2.2]).expand(n, 3).contiguous(),
+        near=torch.full((n,), 1.0), far=torch.full((n,), 3.4), grid_idx=((ii * batch) // n).int(),
+        feature=torch.rand(n, c_in, generator=g), out_sizes=out_sizes, input_sizes=in_sizes,
+        input_grid=torch.randn(rows(in_sizes), c_in, generator=g),
+        mlp_params=sp.mlp_params.detach() + 0.05 * torch.randn(sp.mlp_params.shape, generator=g),
+        n_hidden=sp.n_hidden.numpy(), cfg=np.array([samples, samples_inf, mask_oob, contract]),
+        cot=torch.randn(rows(out_sizes), c_out, generator=g),
+    )

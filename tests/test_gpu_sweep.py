@@ -99,7 +99,7 @@ def test_renderer_sweep_vs_oracle(cfg):
         assert rel_err(a, b) < tol, (cfg, nm, rel_err(a, b))
 
 
-SPLAT_SWEEP = list(itertools.product([False, True], [False, True], [1, 128], [False, True], [None, (3, 64), (4, 32)]))
+SPLAT_SWEEP = list(itertools.product([False, True], [False, True], [1, 128], [False, True], [None, (3, 64), (4, 32), (2, 32)]))
 
 
 @pytest.mark.parametrize("contract,mask,n,triplane,mlp", SPLAT_SWEEP)
@@ -138,5 +138,7 @@ def test_splatter_sweep_vs_oracle(contract, mask, n, triplane, mlp):
     ograds = torch.autograd.grad((oout * f(cot)).sum(), oleaves)
     assert rel_err(out, oout) < 2e-4
     got = [grads[0]] + ([grads[1], torch.cat([g.reshape(-1, feat_dim) for g in grads[2:]], 0)] if mlp else [])
-    for a, b in zip(got, ograds):
-        assert rel_err(a, b) < 2e-4, rel_err(a, b)
+    for i, (a, b) in enumerate(zip(got, ograds)):
+        # [c_in -> 32 -> c_out] runs on the tensor-core path: parameter gradients from bf16 operand tiles
+        tol = 6e-3 if (mlp == (2, 32) and i == 1) else 2e-4
+        assert rel_err(a, b) < tol, (i, rel_err(a, b))

@@ -7,7 +7,8 @@ import subprocess
 import pytest
 import torch
 
-from _golden import case_names, coherent_case, load_case, oracle_render_case, rel_err, synthetic_case
+from _golden import (case_names, coherent_case, load_case, oracle_render_case, oracle_splat_case, rel_err, synthetic_case,
+                     synthetic_splat_case)
 from _lowlevel import render_case, splat_case
 from lightplane_b200 import _cabi
 
@@ -67,3 +68,15 @@ def test_hostsim_renderer_color_grid_tensor_core_path(lib, C, sigma):
     for k, v in got.items():
         tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
         assert rel_err(v, want[k]) < tol, (C, k, rel_err(v, want[k]))
+
+
+@pytest.mark.parametrize("c_in,c_out,triplane", [(16, 16, False), (32, 16, True), (16, 32, True)])
+def test_hostsim_mlp_splatter_tensor_core_path(lib, c_in, c_out, triplane):
+    """MLP splatter [c_in -> 32 -> c_out] on its tensor-core path (lp_splat_tc.cuh)."""
+    c = synthetic_splat_case(n=96, c_in=c_in, c_out=c_out, triplane=triplane)
+    want = oracle_splat_case(c)
+    got = splat_case(lib, c, "cpu")
+    for k, v in got.items():
+        tol = 6e-3 if k == "g_mlp" else 2e-4
+        assert torch.isfinite(v).all(), (k,)
+        assert rel_err(v, want[k]) < tol, (c_in, c_out, k, rel_err(v, want[k]))
