@@ -38,14 +38,15 @@ def main():
     C, P = 16, 64
     shapes = [[1, 1, P, P, C], [1, P, 1, P, C], [1, P, P, 1, C]]
 
-    def renderer(tag, layers, color_grid=False, scaffold=False):
+    def renderer(tag, layers, color_grid=False, scaffold=False, hidden=32, C=C, P=P):
         nt, no, nc = layers
-        dp = lp.init_decoder_params(dev, no, nt, nc, input_chn=C, hidden_chn=32, color_chn=3, opacity_init_bias=-1.0,
+        shapes = [[1, 1, P, P, C], [1, P, 1, P, C], [1, P, P, 1, C]]
+        dp = lp.init_decoder_params(dev, no, nt, nc, input_chn=C, hidden_chn=hidden, color_chn=3, opacity_init_bias=-1.0,
                                     use_separate_color_grid=color_grid)
         dp.mlp_params.requires_grad_(True)
         grids = [(0.5 * torch.randn(s, device=dev)).requires_grad_(True) for s in shapes]
         cgrids = [(0.5 * torch.randn(s, device=dev)).requires_grad_(True) for s in shapes] if color_grid else None
-        enc = torch.randn(n, C if color_grid else 32, device=dev, requires_grad=True)
+        enc = torch.randn(n, C if color_grid else hidden, device=dev, requires_grad=True)
         scaf = (torch.rand(1, 32, 32, 32, device=dev) > 0.5).float() if scaffold else None
         rays = lp.Rays(directions=d, origins=o, grid_idx=gi, near=nr, far=fr, encoding=enc)
         tgt = torch.rand(n, 3, device=dev)
@@ -63,6 +64,8 @@ def main():
     renderer("renderer 2/2/2 + scaffold (tensor-core path)", (2, 2, 2), scaffold=True)
     renderer("renderer 0/2/2 colour grid (tensor-core path)", (0, 2, 2), color_grid=True)
     renderer("renderer 4/2/4 (generic)", (4, 2, 4))
+    renderer("renderer 2/2/2 hidden 64, 128^2x32 planes, scaffold = the reference's example config (generic)", (2, 2, 2),
+             scaffold=True, hidden=64, C=32, P=128)
 
     # MLP splatter: 32^3 x 16 input grid -> 64^3 x 16 output grid
     in_sizes, out_sizes = [(1, 32, 32, 32, 16)], [(1, 64, 64, 64, 16)]
