@@ -21,6 +21,10 @@
 
 #include "lp_render_generic.cuh"
 
+#ifndef LP_TC_EMPTY_FOLD
+#define LP_TC_EMPTY_FOLD 1  // reuse the decoder's zero-feature output at steps where a whole group is in empty space
+#endif
+
 namespace lptc {
 
 constexpr int H = 32;  // hidden width of the decoder shape this path is specialised for
@@ -232,13 +236,15 @@ LP_DEVICE void lp_issue_layer_part(unsigned tbase, int d_col, int a_col, lp_kdes
 
 // the owner thread samples all C channels of its sample point into registers
 // (CW channels starting at ch0: a sample's channels may be split over several threads)
+// Returns whether the sample touches any grid at all (false: acc is exactly zero).
 template <int C, int CW = C>
-LP_DEVICE void lp_gather_regs(const LpGridSet& G, int b, float x, float y, float z, float oob, float (&acc)[CW], int ch0 = 0) {
+LP_DEVICE bool lp_gather_regs(const LpGridSet& G, int b, float x, float y, float z, float oob, float (&acc)[CW], int ch0 = 0) {
+  bool hit = false;
 #pragma unroll
   for (int c = 0; c < CW; ++c) acc[c] = 0.f;
 #ifdef LP_ABL_NO_MEM
   acc[0] = x * y + z;
-  return;
+  return true;
 #endif
   for (int gi = 0; gi < G.n; ++gi) {
     int off[8];
@@ -249,6 +255,7 @@ LP_DEVICE void lp_gather_regs(const LpGridSet& G, int b, float x, float y, float
     for (int tp = 0; tp < 8; ++tp)
       if (tp < nt) wsum += w[tp];
     if (wsum == 0.f) continue;  // the sample misses this grid entirely
+    hit = true;
 #pragma unroll
     for (int tp = 0; tp < 8; ++tp) {
       if (tp < nt) {
@@ -263,6 +270,7 @@ LP_DEVICE void lp_gather_regs(const LpGridSet& G, int b, float x, float y, float
   }
 #pragma unroll
   for (int c = 0; c < CW; ++c) acc[c] *= oob;
+  return hit && oob != 0.f;
 }
 
 // ===========================================================================================
@@ -317,28 +325,42 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
       lp_stage_row<32>(tme + TC_E, e);
     }
     float nlt = 0.f, T = 1.f, acc_len = 0.f, acc_c[3] = {0.f, 0.f, 0.f};
+    // Empty-space folding.  A sample that misses every grid (or is masked out of bounds) has all-zero features,
+    // so the decoder's output there does not depend on the position: it is evaluated once per ray (iteration
+    // step = -1, "probe") and steps at which ALL 128 samples of the group are empty reuse it and skip the three
+    // tensor-core round trips.  The vote rides on the first hand-off's barrier, so other steps pay nothing.
+    float e_raw = 0.f, e_lg0 = 0.f, e_lg1 = 0.f, e_lg2 = 0.f;
 
-    for (int step = 0; step < tot; ++step) {
-      const Sched sc = lp_sched(step, M);
+    for (int step = LP_TC_EMPTY_FOLD ? -1 : 0; step < tot; ++step) {
+      const bool probe = step < 0;
+      const Sched sc = lp_sched(probe ? 0 : step, M);
       float depth, delta;
       lp_depth_delta(sc, me.near, me.far, depth, delta);
       float occ = 1.f;
+      bool hit = false;
       {
-        float x = me.ox + depth * me.dx, y = me.oy + depth * me.dy, z = me.oz + depth * me.dz;
-        if (M.contract) lp_contract(x, y, z);
-        if (SCAF) {  // occupancy scaffold (renderer_fw.py:234-252): a step whose 128 samples are all in
-          occ = lp_nearest(SC, me.b, x, y, z);  // empty space changes nothing and is skipped by the whole group
-          if (!lp_bar_any(1 + grp, GT, occ != 0.f)) continue;
-        }
-        const float oob = M.mask_oob ? lp_in_bounds(x, y, z) : 1.f;
         float x0[C];
-        lp_gather_regs<C>(G, me.b, x, y, z, oob, x0);
+        if (!probe) {
+          float x = me.ox + depth * me.dx, y = me.oy + depth * me.dy, z = me.oz + depth * me.dz;
+          if (M.contract) lp_contract(x, y, z);
+          if (SCAF) {  // occupancy scaffold (renderer_fw.py:234-252): a step whose 128 samples are all in
+            occ = lp_nearest(SC, me.b, x, y, z);  // empty space changes nothing and is skipped by the whole group
+            if (!lp_bar_any(1 + grp, GT, occ != 0.f)) continue;
+          }
+          const float oob = M.mask_oob ? lp_in_bounds(x, y, z) : 1.f;
+          hit = lp_gather_regs<C>(G, me.b, x, y, z, oob, x0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) x0[c] = 0.f;
+        }
         lp_stage_row<C>(tme + TC_A, x0);
       }
+      float raw, lg0, lg1, lg2;
       // ---- trunk layer 0 ----
       lp_tmem_wait_st();
       lp_tc_fence_before();
-      lp_bar_sync(1 + grp, GT);
+      const bool full = LP_TC_EMPTY_FOLD ? (lp_bar_any(1 + grp, GT, hit) || probe) : (lp_bar_sync(1 + grp, GT), true);
+      if (full) {
       if (leader) {
         lp_tc_fence_after();
         lp_issue_layer_part(tbase, TC_D, TC_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, 16, wig);
@@ -381,7 +403,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
       lp_mbar_wait(bar, phase); phase ^= 1;
       lp_tc_fence_after();
       // ---- output layer (4 wide) on the CUDA cores, exact fp32 ----
-      float raw = F[I::FBL + 3], lg0 = F[I::FBL], lg1 = F[I::FBL + 1], lg2 = F[I::FBL + 2];
+      raw = F[I::FBL + 3]; lg0 = F[I::FBL]; lg1 = F[I::FBL + 1]; lg2 = F[I::FBL + 2];
       lp_tmem_ld32u(tme + TC_D, v);
       lp_tmem_zero<32>(tme + TC_D);
 #pragma unroll
@@ -393,6 +415,10 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
         const float hc = fmaxf(v[j] + F[I::FB + 96 + j], 0.f);
         const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
         lg0 = fmaf(hc, w.x, lg0); lg1 = fmaf(hc, w.y, lg1); lg2 = fmaf(hc, w.z, lg2);
+      }
+      if (probe) { e_raw = raw; e_lg0 = lg0; e_lg1 = lg1; e_lg2 = lg2; continue; }
+      } else {
+        raw = e_raw; lg0 = e_lg0; lg1 = e_lg1; lg2 = e_lg2;
       }
       // ---- compositing (renderer_fw.py:289-340) ----
       if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
@@ -794,17 +820,46 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
     };
     Pos cur = sample_at(0), prev = cur;
     float x0[CW], dxp[CW];  // gathered features of the current step; input gradient of the previous step
-    lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
+    bool cur_hit = lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
     bool have_prev = false;
+    // Empty-space folding (see the forward kernel).  With all-zero features every activation of the step is a
+    // per-ray constant and the whole backward sweep is LINEAR in the four compositing gradients (g_raw, dlogit_0..2),
+    // so steps at which all 128 samples of the group are empty only accumulate those four scalars (G, L0..2) and
+    // one extra iteration per ray tile ("virt", step = tot) runs the sweep once with the sums.  Iteration
+    // step = -1 ("probe") evaluates the decoder at zero features for the compositing of the empty steps.
+    float e_raw = 0.f, e_lg0 = 0.f, e_lg1 = 0.f, e_lg2 = 0.f, G_raw = 0.f, L0 = 0.f, L1 = 0.f, L2 = 0.f;
+    bool any_empty = false;
 
-    for (int step = 0; step < tot; ++step) {
+    // compositing gradient of one sample (renderer_bw.py:300-420): marches nlt/T/prefix
+    auto composite = [&](float raw, float lg0, float lg1, float lg2, int step, float& g_raw, float& dl0, float& dl1, float& dl2) {
+      if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
+      const float occ = SCAF ? cur.occ : 1.f;  // compile-time 1 without a scaffold
+      nlt += cur.delta * M.gain * lp_softplus(raw) * occ;
+      const float Tn = expf(-nlt);
+      const float w = T - Tn;
+      T = Tn;
+      const float s0 = lp_sigmoid(lg0), s1 = lp_sigmoid(lg1), s2 = lp_sigmoid(lg2);
+      const float p = fmaf(cur.depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2]))) * occ;
+      prefix = fmaf(w, p, prefix);
+      const float suffix = (step == tot - 1) ? 0.f : total - prefix;
+      const float g_dop = Tn * p - suffix + g_nlt;
+      g_raw = g_dop * cur.delta * M.gain * occ * lp_sigmoid(raw);
+      const float wo = w * occ;
+      dl0 = wo * gF[0] * s0 * (1.f - s0);
+      dl1 = wo * gF[1] * s1 * (1.f - s1);
+      dl2 = wo * gF[2] * s2 * (1.f - s2);
+    };
+
+    for (int step = LP_TC_EMPTY_FOLD ? -1 : 0; step < tot + (LP_TC_EMPTY_FOLD ? 1 : 0); ++step) {
+      const bool probe = step < 0, virt = step == tot, real = !probe && !virt;
+      if (virt && !any_empty) break;
       float v[W];
       // occupancy scaffold (renderer_bw.py, as renderer_fw.py:234-252): a step whose 128 samples are all in empty
       // space has zero weight and zero gradient and is skipped by the whole group (the pipeline just advances)
-      if (SCAF && !lp_bar_any(1 + grp, GTH, cur.occ != 0.f)) {
+      if (SCAF && real && !lp_bar_any(1 + grp, GTH, cur.occ != 0.f)) {
         if (step + 1 < tot) {
           cur = sample_at(step + 1);
-          lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
+          cur_hit = lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
         }
         continue;
       }
@@ -812,12 +867,43 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
 #ifndef LP_ABL_NO_SYNC
       if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
 #endif
-      lp_tile_row<CW>(gs + B::A1, 8 + (CW / 8) * h, s, x0);
-      lp_stage_row<CW, 32>(tme + BT_A + (CW / 2) * h, x0);
+      if (real) {
+        lp_tile_row<CW>(gs + B::A1, 8 + (CW / 8) * h, s, x0);
+        lp_stage_row<CW, 32>(tme + BT_A + (CW / 2) * h, x0);
+      } else {
+        float z0[CW];
+#pragma unroll
+        for (int c = 0; c < CW; ++c) z0[c] = 0.f;
+        lp_tile_row<CW>(gs + B::A1, 8 + (CW / 8) * h, s, z0);
+        lp_stage_row<CW, 32>(tme + BT_A + (CW / 2) * h, z0);
+      }
       // ------------------------------ forward recompute ------------------------------
+#if LP_TC_EMPTY_FOLD && !defined(LP_ABL_NO_SYNC)
+      lp_tmem_wait_st();
+      lp_tc_fence_before();
+      if (!(lp_bar_any(1 + grp, GTH, real && cur_hit) || !real)) {  // every sample of the group is empty
+        float g_raw, dl0, dl1, dl2;
+        composite(e_raw, e_lg0, e_lg1, e_lg2, step, g_raw, dl0, dl1, dl2);
+        G_raw += g_raw; L0 += dl0; L1 += dl1; L2 += dl2;
+        any_empty = true;
+        if (step + 1 < tot) {
+          cur = sample_at(step + 1);
+          cur_hit = lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
+        }
+        continue;
+      }
+      if (leader) {
+        lp_tc_fence_after();
+        LP_ISSUE(BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, true, 32, wi);
+        lp_tc_commit(bar);
+      }
+#else
       LP_TC_HANDOFF(LP_ISSUE(BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, true, 32, wi); lp_tc_commit(bar));
-      if (have_prev && me.active && prev.oob != 0.f)
-        lp_splat_regs<C, CW>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp, CW * h);
+#endif
+      if (have_prev) {
+        if (me.active && prev.oob != 0.f) lp_splat_regs<C, CW>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp, CW * h);
+        have_prev = false;
+      }
       LP_TC_WAIT();
       lp_tmem_ld<W>(tme + BT_D + fc, v);
       LP_TC_ZERO(W, tme + BT_D + fc);
@@ -861,26 +947,14 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
         lg0 += o.x; lg1 += o.y; lg2 += o.z; raw += o.w;
       }
       raw += F[I::FBL + 3]; lg0 += F[I::FBL]; lg1 += F[I::FBL + 1]; lg2 += F[I::FBL + 2];
+      if (probe) {  // decoder output at zero features, for the compositing of the empty steps
+        e_raw = raw; e_lg0 = lg0; e_lg1 = lg1; e_lg2 = lg2;
+        continue;
+      }
       // ------------------------------ compositing gradient ------------------------------
       float g_raw, dl0, dl1, dl2;
-      {
-        if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-        const float occ = SCAF ? cur.occ : 1.f;  // compile-time 1 without a scaffold
-        nlt += cur.delta * M.gain * lp_softplus(raw) * occ;
-        const float Tn = expf(-nlt);
-        const float w = T - Tn;
-        T = Tn;
-        const float s0 = lp_sigmoid(lg0), s1 = lp_sigmoid(lg1), s2 = lp_sigmoid(lg2);
-        const float p = fmaf(cur.depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2]))) * occ;
-        prefix = fmaf(w, p, prefix);
-        const float suffix = (step == tot - 1) ? 0.f : total - prefix;
-        const float g_dop = Tn * p - suffix + g_nlt;
-        g_raw = g_dop * cur.delta * M.gain * occ * lp_sigmoid(raw);
-        const float wo = w * occ;
-        dl0 = wo * gF[0] * s0 * (1.f - s0);
-        dl1 = wo * gF[1] * s1 * (1.f - s1);
-        dl2 = wo * gF[2] * s2 * (1.f - s2);
-      }
+      if (!virt) composite(raw, lg0, lg1, lg2, step, g_raw, dl0, dl1, dl2);
+      else { g_raw = G_raw; dl0 = L0; dl1 = L1; dl2 = L2; }  // the summed gradients of the tile's empty steps
       if (h == 0) lp_tile8(gs + B::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
       // ------------------------------ backward sweep ------------------------------
 #pragma unroll
@@ -899,10 +973,10 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
       lp_tile_row<W>(gs + B::DY, 8 + ck, s, v);
       lp_stage_row<W, 32>(tme + BT_A + 16 + pk, v);
       LP_TC_HANDOFF(LP_ISSUE(BT_A, w_xth, w_xtl, 4, 0, 1024, 32, true, 32, wi); lp_tc_commit(bar));
-      prev = cur;
+      if (!virt) prev = cur;
       if (step + 1 < tot) {  // prefetch the next step's features while the product runs
         cur = sample_at(step + 1);
-        lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
+        cur_hit = lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
       }
       LP_TC_WAIT();
       lp_tmem_ld<W>(tme + BT_D + fc, v);
@@ -924,9 +998,9 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
       LP_TC_ZERO(CW, tme + BT_D + CW * h);
 #pragma unroll
       for (int c = 0; c < CW; ++c) dxp[c] *= prev.oob;
-      have_prev = true;
+      have_prev = !virt;  // (zero features touch no texel: the fold iteration has nothing to scatter)
     }
-    if (me.active && prev.oob != 0.f)  // last step's scatter
+    if (have_prev && me.active && prev.oob != 0.f)  // last step's scatter
       lp_splat_regs<C, CW>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp, CW * h);
     // ---- per-tile tail: encoding gradient = S Wc0^T, and the encoding's share of dWc0 = enc^T S ----
 #ifndef LP_ABL_NO_SYNC
@@ -1021,7 +1095,7 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
 }
 
 #ifndef LP_TC_BWD_NP
-#define LP_TC_BWD_NP 2  // threads per sample in the backward kernel
+#define LP_TC_BWD_NP 1  // threads per sample in the backward kernel (2 halves the registers per thread; measured equal or slower)
 #endif
 template <int C, bool SCAF>
 static int lp_tc_render_backward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {

@@ -112,7 +112,8 @@ def oracle_splat_case(c, dtype=torch.float64):
     return {k: v.detach() for k, v in res.items()}
 
 
-def coherent_case(c, n=64, pixel=0.02, seed=5, batch_blocks=True, mask_oob=None, plane=None, scaffold_res=None):
+def coherent_case(c, n=64, pixel=0.02, seed=5, batch_blocks=True, mask_oob=None, plane=None, scaffold_res=None,
+                  origin=(0.1, -0.15, -2.2), near=1.0, far=3.4):
     """A copy of golden case `c` whose rays are replaced by `n` neighbouring pixels of a pinhole camera
     (the layout real renders have, and the one the backward kernel's warp-level scatter aggregation is
     built for); expected values then come from the oracle.  `plane`: optionally resize every grid to
@@ -124,9 +125,9 @@ def coherent_case(c, n=64, pixel=0.02, seed=5, batch_blocks=True, mask_oob=None,
     px, py = (ii % w).float() - w / 2, (ii // w).float() - w / 2
     d = torch.stack([px * pixel + 0.03, py * pixel - 0.02, torch.ones(n)], -1)
     c["directions"] = d / d.norm(dim=-1, keepdim=True)
-    c["origins"] = torch.tensor([0.1, -0.15, -2.2]).expand(n, 3).contiguous()
-    c["near"] = torch.full((n,), 1.0)
-    c["far"] = torch.full((n,), 3.4)
+    c["origins"] = torch.tensor(list(origin)).expand(n, 3).contiguous()
+    c["near"] = torch.full((n,), float(near))
+    c["far"] = torch.full((n,), float(far))
     B = int(c["grid_sizes"][0][0])
     c["grid_idx"] = ((ii * B) // n).int() if batch_blocks else torch.randint(0, B, (n,), generator=g).int()
     c["encoding"] = torch.randn(n, c["encoding"].shape[1], generator=g)

@@ -71,6 +71,19 @@ def test_renderer_scaffold_tensor_core_path(lib, name, n, pixel, plane, mask, sc
     test_renderer_coherent_rays_vs_oracle(lib, name, n, pixel, plane, mask, scaf)
 
 
+@pytest.mark.parametrize("name,n,mask", [("render_triplane_inf_gain", 1500, 0), ("render_c32_b1", 700, 1)])
+def test_renderer_empty_space_folding(lib, name, n, mask):
+    """Rays that start and end far outside the volume: at many steps all samples of a group miss every plane, the
+    case the tensor-core kernels fold (decoder evaluated once at zero features, summed compositing gradients)."""
+    c = coherent_case(load_case(name), n=n, pixel=0.002, mask_oob=mask, plane=48, origin=(0.4, -0.2, -3.0), near=0.3,
+                      far=6.0)
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cuda")
+    for k, v in got.items():
+        tol = TOL_GMLP_TINY if k == "g_mlp" else (TOL_GRAD if k.startswith("g_") else TOL)
+        assert rel_err(v, want[k]) < tol, (name, k, rel_err(v, want[k]))
+
+
 @pytest.mark.parametrize("C,n,plane,sigma", [(16, 2048, 48, 0.0), (32, 777, 40, 0.5)])
 def test_renderer_color_grid_tensor_core_path(lib, C, n, plane, sigma):
     """Separate colour grid ("ReLU field", trunk-less decoder, hidden 32) on its tensor-core path."""
