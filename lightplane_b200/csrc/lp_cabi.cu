@@ -10,6 +10,7 @@
 #include "lp_render_tc.cuh"
 #include "lp_render_tc_cg.cuh"
 #include "lp_splat_tc.cuh"
+#include "lp_render_tc_wide.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -239,6 +240,12 @@ int lp_render_forward(void* stream, const lp_march_cfg* cfg, const lp_decoder_sp
                                          features_stride)))
       LP_FAIL(rc, "colour-grid forward launch setup failed");
     return lp_check_launch("lp_render_forward(colour grid)");
+  }
+  if (lptc::lp_tcw_forward_supported(a)) {
+    if ((rc = lptc::lp_tcw_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance, out_features,
+                                          features_stride)))
+      LP_FAIL(rc, "hidden-64 forward launch setup failed");
+    return lp_check_launch("lp_render_forward(hidden 64)");
   }
   const int pf = (a.D.n_params + 3) & ~3;
   const int per_warp = (a.A.total + a.D.in_c + a.D.n_feat) * LP_LS;

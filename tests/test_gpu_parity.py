@@ -84,6 +84,22 @@ def test_renderer_empty_space_folding(lib, name, n, mask):
         assert rel_err(v, want[k]) < tol, (name, k, rel_err(v, want[k]))
 
 
+@pytest.mark.parametrize("C,n,plane,scaf", [(32, 1500, 48, None), (16, 900, 40, 10)])
+def test_renderer_hidden64_forward(lib, C, n, plane, scaf):
+    """Hidden width 64 (the reference's example configuration): tensor-core forward, generic (fp32) backward."""
+    c = synthetic_case(n=n, C=C, hidden=64, layers=(2, 2, 2), color_grid=False, plane=plane, samples=24, samples_inf=3,
+                       pixel=0.004, batch=1)
+    if scaf:
+        c = coherent_case(c, n=n, pixel=0.004, seed=3, scaffold_res=scaf)
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cuda")
+    for k, v in got.items():
+        # the fp32 backward recomputes the march from outputs saved by the tensor-core forward (1e-5 apart from its own
+        # arithmetic), which shows in total - prefix: gradients get the tensor-core tolerance
+        tol = TOL_GRAD if k.startswith("g_") else TOL
+        assert rel_err(v, want[k]) < tol, (C, k, rel_err(v, want[k]))
+
+
 @pytest.mark.parametrize("C,n,plane,sigma", [(16, 2048, 48, 0.0), (32, 777, 40, 0.5)])
 def test_renderer_color_grid_tensor_core_path(lib, C, n, plane, sigma):
     """Separate colour grid ("ReLU field", trunk-less decoder, hidden 32) on its tensor-core path."""

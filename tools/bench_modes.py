@@ -57,14 +57,19 @@ def main():
             _, _, f = lp.lightplane_renderer(rays, grids, dp, num_samples=a.samples, gain=1.0, color_grid=cgrids, scaffold=scaf)
             ((f - tgt) ** 2).sum().backward()
 
-        ms = timed(step)
-        print(json.dumps({"mode": tag, "rays": n, "samples": a.samples, "ms_fwd_bwd": ms, "rays_per_s": n / ms * 1e3}))
+        def fwd_only():
+            with torch.no_grad():
+                lp.lightplane_renderer(rays, grids, dp, num_samples=a.samples, gain=1.0, color_grid=cgrids, scaffold=scaf)
+
+        ms, ms_f = timed(step), timed(fwd_only)
+        print(json.dumps({"mode": tag, "rays": n, "samples": a.samples, "ms_fwd_bwd": ms, "rays_per_s": n / ms * 1e3,
+                          "ms_fwd_only": ms_f, "fwd_rays_per_s": n / ms_f * 1e3}))
 
     renderer("renderer 2/2/2 (tensor-core path)", (2, 2, 2))
     renderer("renderer 2/2/2 + scaffold (tensor-core path)", (2, 2, 2), scaffold=True)
     renderer("renderer 0/2/2 colour grid (tensor-core path)", (0, 2, 2), color_grid=True)
     renderer("renderer 4/2/4 (generic)", (4, 2, 4))
-    renderer("renderer 2/2/2 hidden 64, 128^2x32 planes, scaffold = the reference's example config (generic)", (2, 2, 2),
+    renderer("renderer 2/2/2 hidden 64, 128^2x32 planes, scaffold = the reference's example config (tensor-core forward, generic backward)", (2, 2, 2),
              scaffold=True, hidden=64, C=32, P=128)
 
     # MLP splatter: 32^3 x 16 input grid -> 64^3 x 16 output grid
