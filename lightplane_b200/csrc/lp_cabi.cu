@@ -291,6 +291,10 @@ int lp_render_backward(void* stream, const lp_march_cfg* cfg, const lp_decoder_s
     if ((rc = lptc::lp_cg_render_backward(st, a, mlp_params, io))) LP_FAIL(rc, "colour-grid backward launch setup failed");
     return lp_check_launch("lp_render_backward(colour grid)");
   }
+  if (lptc::lp_tcw_forward_supported(a)) {
+    if ((rc = lptc::lp_tcw_render_backward(st, a, mlp_params, io))) LP_FAIL(rc, "hidden-64 backward launch setup failed");
+    return lp_check_launch("lp_render_backward(hidden 64)");
+  }
   const int pf = (a.D.n_params + 3) & ~3;
   const int per_warp = (a.A.total + 3 * a.D.max_dim + 2 * a.D.in_c + a.D.n_feat) * LP_LS;
   int warps, pin; size_t bytes;

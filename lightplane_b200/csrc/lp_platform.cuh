@@ -139,6 +139,20 @@ LP_DEVICE void lp_tc_mma_ts(bool tf32, unsigned d_taddr, unsigned a_taddr, unsig
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d_taddr), "r"(a_taddr), "r"(b_lo),
                  "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// TS MMA whose B operand is a K-major weight tile read TRANSPOSED (as an MN-major operand, b_major = 1): for a
+// tile [n][k] with n-chunk stride `nstride`, B'[n' = k][k' = n] sits at (k'/8)*nstride + (n'/8)*128 + (k'%8)*16 +
+// (n'%8)*2, i.e. descriptor field 1 (K-group stride) = nstride, field 2 (MN-chunk stride) = 128; one MMA consumes 16
+// values of k' = two n-chunks of the tile (advance the start address by 2*nstride).  tools/tc_test3.cu, phase 2.
+LP_DEVICE lp_kdesc_t lp_tc_kdesc_lo_t(const void* smem_ptr, int nstride) {
+  return ((lp_smem_u32(smem_ptr) >> 4) & 0x3FFF) | ((unsigned)(nstride >> 4) << 16);
+}
+LP_DEVICE void lp_tc_mma_ts_t(unsigned d_taddr, unsigned a_taddr, lp_kdesc_t b_lo, int nstride, int n, int accumulate) {
+  const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((unsigned)(n >> 3) << 17) | (8u << 24);
+  const unsigned hi = 8u | (1u << 14);
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 db, {%2, %3};\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d_taddr), "r"(a_taddr), "r"(b_lo),
+               "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 // both operands in shared memory, bf16, MN-major, no swizzle, K-group stride 128 B, MN-chunk stride `sbo`:
 // element (mn, k) at (mn/8)*sbo + (k/8)*128 + (k%8)*16 + (mn%8)*2.  D(128 x n) (+)= A(128 x 16) * B(16 x n).
 LP_DEVICE lp_kdesc_t lp_tc_mndesc_lo(const void* smem_ptr) { return ((lp_smem_u32(smem_ptr) >> 4) & 0x3FFF) | (8u << 16); }

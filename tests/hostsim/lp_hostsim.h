@@ -281,6 +281,26 @@ static inline void lp_tc_mma_ts(bool tf32, unsigned d_taddr, unsigned a_taddr, c
     }
   }
 }
+static inline lp_kdesc_t lp_tc_kdesc_lo_t(const void* smem_ptr, int) { return static_cast<const unsigned char*>(smem_ptr); }
+static inline void lp_tc_mma_ts_t(unsigned d_taddr, unsigned a_taddr, lp_kdesc_t b, int nstride, int n, int accumulate) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  float* T = lp_hostsim::g_ctx->block->tmem;
+  const int dcol = d_taddr & 0xffff, acol = a_taddr & 0xffff;
+  for (int m = 0; m < 128; ++m) {
+    float a[16];
+    for (int k = 0; k < 16; ++k) {
+      const unsigned w = lp_hs_tmem_word(m, acol + k / 2);
+      const unsigned u = (k & 1) ? (w & 0xffff0000u) : (w << 16);
+      std::memcpy(&a[k], &u, 4);
+    }
+    for (int j = 0; j < n; ++j) {
+      float acc = accumulate ? T[m * 512 + dcol + j] : 0.f;
+      for (int k = 0; k < 16; ++k) acc += a[k] * lp_hs_bf16(b, (k / 8) * nstride + (j / 8) * 128 + (k % 8) * 16 + (j % 8) * 2);
+      T[m * 512 + dcol + j] = acc;
+    }
+  }
+}
 static inline lp_kdesc_t lp_tc_mndesc_lo(const void* smem_ptr) { return static_cast<const unsigned char*>(smem_ptr); }
 static inline void lp_tc_mma_ss_mn(unsigned d_taddr, lp_kdesc_t a, lp_kdesc_t b, int sbo, int n, int accumulate) {
   static std::mutex mu;

@@ -96,11 +96,12 @@ def test_hostsim_renderer_empty_space_folding(lib, name, mask):
 
 @pytest.mark.parametrize("C,sigma,scaf", [(32, 0.0, None), (16, 0.5, 6)])
 def test_hostsim_renderer_hidden64_forward(lib, C, sigma, scaf):
-    """Hidden width 64 (the reference's example configuration): tensor-core forward (lp_render_tc_wide.cuh), generic backward."""
+    """Hidden width 64 (the reference's example configuration): lp_render_tc_wide.cuh."""
     c = synthetic_case(n=96, C=C, hidden=64, layers=(2, 2, 2), color_grid=False, sigma=sigma)
     if scaf:
         c = coherent_case(c, n=96, pixel=0.03, seed=3, scaffold_res=scaf)
     want = oracle_render_case(c)
     got = render_case(lib, c, "cpu")
     for k, v in got.items():
-        assert rel_err(v, want[k]) < (1e-3 if k.startswith("g_") else 2e-4), (C, k, rel_err(v, want[k]))
+        tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
+        assert rel_err(v, want[k]) < tol, (C, k, rel_err(v, want[k]))
