@@ -11,6 +11,7 @@
 #include "lp_render_tc_cg.cuh"
 #include "lp_splat_tc.cuh"
 #include "lp_render_tc_wide.cuh"
+#include "lp_render_tc_deep.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -247,6 +248,13 @@ int lp_render_forward(void* stream, const lp_march_cfg* cfg, const lp_decoder_sp
       LP_FAIL(rc, "hidden-64 forward launch setup failed");
     return lp_check_launch("lp_render_forward(hidden 64)");
   }
+  lptc::DeepPlan dpl;
+  if (lptc::lp_deep_plan(a, &dpl)) {
+    if ((rc = lptc::lp_deep_render_forward(st, a, dpl, mlp_params, out_ray_length, out_neg_log_transmittance, out_features,
+                                           features_stride)))
+      LP_FAIL(rc, "layer-count-general forward launch setup failed");
+    return lp_check_launch("lp_render_forward(deep)");
+  }
   const int pf = (a.D.n_params + 3) & ~3;
   const int per_warp = (a.A.total + a.D.in_c + a.D.n_feat) * LP_LS;
   int warps, pin; size_t bytes;
@@ -294,6 +302,11 @@ int lp_render_backward(void* stream, const lp_march_cfg* cfg, const lp_decoder_s
   if (lptc::lp_tcw_forward_supported(a)) {
     if ((rc = lptc::lp_tcw_render_backward(st, a, mlp_params, io))) LP_FAIL(rc, "hidden-64 backward launch setup failed");
     return lp_check_launch("lp_render_backward(hidden 64)");
+  }
+  lptc::DeepPlan dpl;
+  if (lptc::lp_deep_plan(a, &dpl)) {
+    if ((rc = lptc::lp_deep_render_backward(st, a, dpl, mlp_params, io))) LP_FAIL(rc, "layer-count-general backward launch setup failed");
+    return lp_check_launch("lp_render_backward(deep)");
   }
   const int pf = (a.D.n_params + 3) & ~3;
   const int per_warp = (a.A.total + 3 * a.D.max_dim + 2 * a.D.in_c + a.D.n_feat) * LP_LS;

@@ -98,6 +98,25 @@ def test_renderer_hidden64(lib, C, n, plane, scaf):
         assert rel_err(v, want[k]) < tol, (C, k, rel_err(v, want[k]))
 
 
+@pytest.mark.parametrize("layers,C,n,scaf", [((4, 2, 4), 16, 1500, None), ((2, 4, 2), 32, 700, 10), ((1, 1, 1), 16, 900, None),
+                                              ((3, 1, 2), 32, 600, None), ((1, 3, 1), 16, 500, None)])
+def test_renderer_layer_counts_tensor_core_path(lib, layers, C, n, scaf):
+    """Layer counts other than 2/2/2 (hidden 32): the table-driven tensor-core kernels of lp_render_tc_deep.cuh."""
+    c = synthetic_case(n=n, C=C, hidden=32, layers=layers, color_grid=False, plane=40, samples=24, samples_inf=3, pixel=0.004,
+                       batch=1)
+    if scaf:
+        c = coherent_case(c, n=n, pixel=0.004, seed=3, scaffold_res=scaf)
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cuda")
+    for k, v in got.items():
+        # deeper decoders: more ReLU gates whose pre-activation (accurate to ~1e-5 of the summed terms with the bf16 hi+lo
+        # products) lies within rounding of zero; a flipped gate is an O(1) error of that sample's gradient (SURVEY 8d:
+        # "max norm is noisy: ReLU-gate flips").  Measured 1-2e-3 on these random decoders with 6-8 hidden layers (the host
+        # emulation gives the same figure, i.e. arithmetic, not a race); 2/2/2 stays at 2e-5..2e-4.
+        tol = TOL_GMLP_TINY if k == "g_mlp" else (3e-3 if k.startswith("g_") else TOL)
+        assert rel_err(v, want[k]) < tol, (layers, k, rel_err(v, want[k]))
+
+
 @pytest.mark.parametrize("C,n,plane,sigma", [(16, 2048, 48, 0.0), (32, 777, 40, 0.5)])
 def test_renderer_color_grid_tensor_core_path(lib, C, n, plane, sigma):
     """Separate colour grid ("ReLU field", trunk-less decoder, hidden 32) on its tensor-core path."""

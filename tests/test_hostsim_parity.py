@@ -105,3 +105,15 @@ def test_hostsim_renderer_hidden64_forward(lib, C, sigma, scaf):
     for k, v in got.items():
         tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
         assert rel_err(v, want[k]) < tol, (C, k, rel_err(v, want[k]))
+
+
+@pytest.mark.parametrize("layers,C,sigma", [((4, 2, 4), 16, 0.0), ((2, 4, 2), 32, 0.5), ((1, 1, 1), 16, 0.0), ((3, 1, 2), 32, 0.0),
+                                            ((1, 3, 1), 16, 0.0)])
+def test_hostsim_renderer_layer_counts_tensor_core_path(lib, layers, C, sigma):
+    """Layer counts other than 2/2/2 (hidden 32): the table-driven tensor-core kernels of lp_render_tc_deep.cuh."""
+    c = synthetic_case(n=96, C=C, hidden=32, layers=layers, color_grid=False, sigma=sigma)
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cpu")
+    for k, v in got.items():
+        tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
+        assert rel_err(v, want[k]) < tol, (layers, k, rel_err(v, want[k]))

@@ -68,7 +68,8 @@ def main():
     renderer("renderer 2/2/2 (tensor-core path)", (2, 2, 2))
     renderer("renderer 2/2/2 + scaffold (tensor-core path)", (2, 2, 2), scaffold=True)
     renderer("renderer 0/2/2 colour grid (tensor-core path)", (0, 2, 2), color_grid=True)
-    renderer("renderer 4/2/4 (generic)", (4, 2, 4))
+    renderer("renderer 4/2/4 (tensor-core path, table driven)", (4, 2, 4))
+    renderer("renderer 4/4/4 (generic)", (4, 4, 4))
     renderer("renderer 2/2/2 hidden 64, 128^2x32 planes, scaffold = the reference's example config (tensor-core path)", (2, 2, 2),
              scaffold=True, hidden=64, C=32, P=128)
 
