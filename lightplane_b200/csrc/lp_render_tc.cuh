@@ -84,6 +84,61 @@ LP_DEVICE void lp_depth_delta(const Sched& s, float near, float far, float& dept
   }
 }
 
+// ---- compositing of one sample, shared by every tensor-core renderer kernel ----
+// forward (renderer_fw.py:289-340): NLT += delta*gain*softplus(raw)*occ; w = T_prev - T; len += w*depth; feat += w*occ*sigmoid(logit)
+struct LpCompFwd {
+  float nlt = 0.f, T = 1.f, len = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  LP_DEVICE void add(const LpMarch& M, int ray, int step, float raw, float lg0, float lg1, float lg2, float depth, float delta, float occ) {
+    if (M.noise) raw += M.sigma * lp_sample_noise(M, ray, step);
+    nlt += delta * M.gain * lp_softplus(raw) * occ;
+    const float Tn = expf(-nlt);
+    const float w = T - Tn;
+    T = Tn;
+    len = fmaf(w, depth, len);
+    const float wc = w * occ;
+    c0 = fmaf(wc, lp_sigmoid(lg0), c0);
+    c1 = fmaf(wc, lp_sigmoid(lg1), c1);
+    c2 = fmaf(wc, lp_sigmoid(lg2), c2);
+  }
+};
+// backward (renderer_bw.py:300-420), marching FORWARD with the saved outputs: with p_j = depth_j g_len + sum_c sigmoid_c gF_c,
+// total = sum_j w_j p_j (from the saved outputs) and prefix_j = sum_{k<=j} w_k p_k,
+//   dL/d(delta gain o_j) = T_j p_j - (total - prefix_j) + g_nlt      (the bracket is forced to 0 behind the last sample)
+struct LpCompBwd {
+  float g_len, g_nlt, gF[3], total;   // per-ray constants
+  float nlt = 0.f, T = 1.f, prefix = 0.f;
+  LP_DEVICE void init(const LpBwdIo& io, int q, bool active, int n_feat) {
+    g_len = active ? io.g_len[q] : 0.f;
+    g_nlt = active ? io.g_nlt[q] : 0.f;
+    total = g_len * io.len[q];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      gF[c] = (active && c < n_feat) ? io.g_feat[(long long)q * io.g_feat_stride + c] : 0.f;
+      if (c < n_feat) total = fmaf(gF[c], io.feat[(long long)q * io.feat_stride + c], total);
+    }
+    nlt = 0.f; T = 1.f; prefix = 0.f;
+  }
+  // returns the gradients of the raw opacity and of the three colour logits
+  LP_DEVICE void grad(const LpMarch& M, int ray, int step, bool last, float raw, float lg0, float lg1, float lg2, float depth, float delta,
+                      float occ, float& g_raw, float& dl0, float& dl1, float& dl2) {
+    if (M.noise) raw += M.sigma * lp_sample_noise(M, ray, step);
+    nlt += delta * M.gain * lp_softplus(raw) * occ;
+    const float Tn = expf(-nlt);
+    const float w = T - Tn;
+    T = Tn;
+    const float s0 = lp_sigmoid(lg0), s1 = lp_sigmoid(lg1), s2 = lp_sigmoid(lg2);
+    const float p = fmaf(depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2]))) * occ;
+    prefix = fmaf(w, p, prefix);
+    const float suffix = last ? 0.f : total - prefix;
+    const float g_dop = Tn * p - suffix + g_nlt;
+    g_raw = g_dop * delta * M.gain * occ * lp_sigmoid(raw);
+    const float wo = w * occ;
+    dl0 = wo * gF[0] * s0 * (1.f - s0);
+    dl1 = wo * gF[1] * s1 * (1.f - s1);
+    dl2 = wo * gF[2] * s2 * (1.f - s2);
+  }
+};
+
 // taps of one grid with 32-bit element offsets (the fast path requires < 2^31 grid elements)
 LP_DEVICE void lp_axis_i(float p, int size, int& i0, float& frac) {
   float i = ((p + 1.f) * 0.5f) * (float)size - 0.5f;
@@ -324,7 +379,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
       }
       lp_stage_row<32>(tme + TC_E, e);
     }
-    float nlt = 0.f, T = 1.f, acc_len = 0.f, acc_c[3] = {0.f, 0.f, 0.f};
+    LpCompFwd cf;
     // Empty-space folding.  A sample that misses every grid (or is masked out of bounds) has all-zero features,
     // so the decoder's output there does not depend on the position: it is evaluated once per ray (iteration
     // step = -1, "probe") and steps at which ALL 128 samples of the group are empty reuse it and skip the three
@@ -421,21 +476,12 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMa
         raw = e_raw; lg0 = e_lg0; lg1 = e_lg1; lg2 = e_lg2;
       }
       // ---- compositing (renderer_fw.py:289-340) ----
-      if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-      nlt += SCAF ? delta * M.gain * lp_softplus(raw) * occ : delta * M.gain * lp_softplus(raw);
-      const float Tn = expf(-nlt);
-      const float w = T - Tn;
-      T = Tn;
-      acc_len = fmaf(w, depth, acc_len);
-      const float wc = SCAF ? w * occ : w;
-      acc_c[0] = fmaf(wc, lp_sigmoid(lg0), acc_c[0]);
-      acc_c[1] = fmaf(wc, lp_sigmoid(lg1), acc_c[1]);
-      acc_c[2] = fmaf(wc, lp_sigmoid(lg2), acc_c[2]);
+      cf.add(M, me.ray, step, raw, lg0, lg1, lg2, depth, delta, occ);
     }
     if (me.active) {
-      out_len[me.ray] = acc_len;
-      out_nlt[me.ray] = nlt;
-      for (int c = 0; c < D.n_feat; ++c) out_feat[(long long)me.ray * feat_stride + c] = acc_c[c];
+      out_len[me.ray] = cf.len;
+      out_nlt[me.ray] = cf.nlt;
+      for (int c = 0; c < D.n_feat; ++c) out_feat[(long long)me.ray * feat_stride + c] = c == 0 ? cf.c0 : (c == 1 ? cf.c1 : cf.c2);
     }
   }
   lp_tc_fence_before();
@@ -791,15 +837,8 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
       }
       lp_stage_row<W, 16>(tme + BT_E + pk, e);
     }
-    // per-ray constants of the compositing gradient (renderer_bw.py:300-420)
-    const float g_len = me.active ? io.g_len[q] : 0.f, g_nlt = me.active ? io.g_nlt[q] : 0.f;
-    float gF[3], total = g_len * io.len[q];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      gF[c] = (me.active && c < D.n_feat) ? io.g_feat[(long long)q * io.g_feat_stride + c] : 0.f;
-      if (c < D.n_feat) total = fmaf(gF[c], io.feat[(long long)q * io.feat_stride + c], total);
-    }
-    float nlt = 0.f, T = 1.f, prefix = 0.f;
+    LpCompBwd cb;  // per-ray constants and running state of the compositing gradient
+    cb.init(io, q, me.active, D.n_feat);
     float S[W];  // sum over steps of the colour-hidden gradient (this part's columns)
 #pragma unroll
     for (int j = 0; j < W; ++j) S[j] = 0.f;
@@ -830,24 +869,8 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
     float e_raw = 0.f, e_lg0 = 0.f, e_lg1 = 0.f, e_lg2 = 0.f, G_raw = 0.f, L0 = 0.f, L1 = 0.f, L2 = 0.f;
     bool any_empty = false;
 
-    // compositing gradient of one sample (renderer_bw.py:300-420): marches nlt/T/prefix
     auto composite = [&](float raw, float lg0, float lg1, float lg2, int step, float& g_raw, float& dl0, float& dl1, float& dl2) {
-      if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-      const float occ = SCAF ? cur.occ : 1.f;  // compile-time 1 without a scaffold
-      nlt += cur.delta * M.gain * lp_softplus(raw) * occ;
-      const float Tn = expf(-nlt);
-      const float w = T - Tn;
-      T = Tn;
-      const float s0 = lp_sigmoid(lg0), s1 = lp_sigmoid(lg1), s2 = lp_sigmoid(lg2);
-      const float p = fmaf(cur.depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2]))) * occ;
-      prefix = fmaf(w, p, prefix);
-      const float suffix = (step == tot - 1) ? 0.f : total - prefix;
-      const float g_dop = Tn * p - suffix + g_nlt;
-      g_raw = g_dop * cur.delta * M.gain * occ * lp_sigmoid(raw);
-      const float wo = w * occ;
-      dl0 = wo * gF[0] * s0 * (1.f - s0);
-      dl1 = wo * gF[1] * s1 * (1.f - s1);
-      dl2 = wo * gF[2] * s2 * (1.f - s2);
+      cb.grad(M, me.ray, step, step == tot - 1, raw, lg0, lg1, lg2, cur.depth, cur.delta, SCAF ? cur.occ : 1.f, g_raw, dl0, dl1, dl2);
     };
 
     for (int step = LP_TC_EMPTY_FOLD ? -1 : 0; step < tot + (LP_TC_EMPTY_FOLD ? 1 : 0); ++step) {

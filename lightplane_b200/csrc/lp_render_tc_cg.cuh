@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_cg_kernel(LpRays R, LpMa
         enc[4 * k] = v.x; enc[4 * k + 1] = v.y; enc[4 * k + 2] = v.z; enc[4 * k + 3] = v.w;
       }
     }
-    float nlt = 0.f, T = 1.f, acc_len = 0.f, acc_c[3] = {0.f, 0.f, 0.f};
+    LpCompFwd cf;
     for (int step = 0; step < tot; ++step) {
       const Sched sc = lp_sched(step, M);
       float depth, delta;
@@ -161,20 +161,12 @@ __global__ void __launch_bounds__(512, 1) lp_render_fwd_cg_kernel(LpRays R, LpMa
         const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
         lg0 = fmaf(hc, w.x, lg0); lg1 = fmaf(hc, w.y, lg1); lg2 = fmaf(hc, w.z, lg2);
       }
-      if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-      nlt += delta * M.gain * lp_softplus(raw);
-      const float Tn = expf(-nlt);
-      const float w = T - Tn;
-      T = Tn;
-      acc_len = fmaf(w, depth, acc_len);
-      acc_c[0] = fmaf(w, lp_sigmoid(lg0), acc_c[0]);
-      acc_c[1] = fmaf(w, lp_sigmoid(lg1), acc_c[1]);
-      acc_c[2] = fmaf(w, lp_sigmoid(lg2), acc_c[2]);
+      cf.add(M, me.ray, step, raw, lg0, lg1, lg2, depth, delta, 1.f);
     }
     if (me.active) {
-      out_len[me.ray] = acc_len;
-      out_nlt[me.ray] = nlt;
-      for (int c = 0; c < D.n_feat; ++c) out_feat[(long long)me.ray * feat_stride + c] = acc_c[c];
+      out_len[me.ray] = cf.len;
+      out_nlt[me.ray] = cf.nlt;
+      for (int c = 0; c < D.n_feat; ++c) out_feat[(long long)me.ray * feat_stride + c] = c == 0 ? cf.c0 : (c == 1 ? cf.c1 : cf.c2);
     }
   }
   lp_tc_fence_before();
@@ -274,14 +266,8 @@ __global__ void __launch_bounds__(384, 1) lp_render_bwd_cg_kernel(LpRays R, LpMa
 #pragma unroll
       for (int c = 0; c < C; ++c) genc[c] = 0.f;
     }
-    const float g_len = me.active ? io.g_len[q] : 0.f, g_nlt = me.active ? io.g_nlt[q] : 0.f;
-    float gF[3], total = g_len * io.len[q];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      gF[c] = (me.active && c < D.n_feat) ? io.g_feat[(long long)q * io.g_feat_stride + c] : 0.f;
-      if (c < D.n_feat) total = fmaf(gF[c], io.feat[(long long)q * io.feat_stride + c], total);
-    }
-    float nlt = 0.f, T = 1.f, prefix = 0.f;
+    LpCompBwd cb;
+    cb.init(io, q, me.active, D.n_feat);
 
     for (int step = 0; step < tot; ++step) {
       const Sched sc = lp_sched(step, M);
@@ -323,22 +309,7 @@ __global__ void __launch_bounds__(384, 1) lp_render_bwd_cg_kernel(LpRays R, LpMa
       lp_tile_row<32>(gs + I::A2, 4, s, v);
       // ------------------------------ compositing gradient (as lp_render_bwd_tc_kernel) ------------------------------
       float g_raw, dl0, dl1, dl2;
-      {
-        if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-        nlt += delta * M.gain * lp_softplus(raw);
-        const float Tn = expf(-nlt);
-        const float w = T - Tn;
-        T = Tn;
-        const float s0 = lp_sigmoid(lg0), s1 = lp_sigmoid(lg1), s2 = lp_sigmoid(lg2);
-        const float p = fmaf(depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2])));
-        prefix = fmaf(w, p, prefix);
-        const float suffix = (step == tot - 1) ? 0.f : total - prefix;
-        const float g_dop = Tn * p - suffix + g_nlt;
-        g_raw = g_dop * delta * M.gain * lp_sigmoid(raw);
-        dl0 = w * gF[0] * s0 * (1.f - s0);
-        dl1 = w * gF[1] * s1 * (1.f - s1);
-        dl2 = w * gF[2] * s2 * (1.f - s2);
-      }
+      cb.grad(M, me.ray, step, step == tot - 1, raw, lg0, lg1, lg2, depth, delta, 1.f, g_raw, dl0, dl1, dl2);
       lp_tile8(gs + I::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
       // ------------------------------ backward sweep ------------------------------
 #pragma unroll

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256, 1) lp_render_fwd_deep_kernel(LpRays R, Lp
       dp_load_enc(R, q, e);
       lp_stage_row<32, 16>(tme + DT_E, e);
     }
-    float nlt = 0.f, T = 1.f, acc_len = 0.f, acc_c[3] = {0.f, 0.f, 0.f};
+    LpCompFwd cf;
     for (int step = 0; step < tot; ++step) {
       const Sched sc = lp_sched(step, M);
       float depth, delta;
@@ -199,21 +199,12 @@ __global__ void __launch_bounds__(256, 1) lp_render_fwd_deep_kernel(LpRays R, Lp
         dp_logits(F, e, lg0, lg1, lg2);
       }
       raw += F[I::FBL + 3]; lg0 += F[I::FBL]; lg1 += F[I::FBL + 1]; lg2 += F[I::FBL + 2];
-      if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-      nlt += SCAF ? delta * M.gain * lp_softplus(raw) * occ : delta * M.gain * lp_softplus(raw);
-      const float Tn = expf(-nlt);
-      const float w = T - Tn;
-      T = Tn;
-      acc_len = fmaf(w, depth, acc_len);
-      const float wc = SCAF ? w * occ : w;
-      acc_c[0] = fmaf(wc, lp_sigmoid(lg0), acc_c[0]);
-      acc_c[1] = fmaf(wc, lp_sigmoid(lg1), acc_c[1]);
-      acc_c[2] = fmaf(wc, lp_sigmoid(lg2), acc_c[2]);
+      cf.add(M, me.ray, step, raw, lg0, lg1, lg2, depth, delta, occ);
     }
     if (me.active) {
-      out_len[me.ray] = acc_len;
-      out_nlt[me.ray] = nlt;
-      for (int c = 0; c < pl.n_feat; ++c) out_feat[(long long)me.ray * feat_stride + c] = acc_c[c];
+      out_len[me.ray] = cf.len;
+      out_nlt[me.ray] = cf.nlt;
+      for (int c = 0; c < pl.n_feat; ++c) out_feat[(long long)me.ray * feat_stride + c] = c == 0 ? cf.c0 : (c == 1 ? cf.c1 : cf.c2);
     }
   }
   lp_tc_fence_before();
@@ -309,14 +300,8 @@ __global__ void __launch_bounds__(128, 1) lp_render_bwd_deep_kernel(LpRays R, Lp
       dp_load_enc(R, q, e);
       lp_stage_row<32, 16>(tme + DT_E, e);
     }
-    const float g_len = me.active ? io.g_len[q] : 0.f, g_nlt = me.active ? io.g_nlt[q] : 0.f;
-    float gF[3], total = g_len * io.len[q];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      gF[c] = (me.active && c < pl.n_feat) ? io.g_feat[(long long)q * io.g_feat_stride + c] : 0.f;
-      if (c < pl.n_feat) total = fmaf(gF[c], io.feat[(long long)q * io.feat_stride + c], total);
-    }
-    float nlt = 0.f, T = 1.f, prefix = 0.f;
+    LpCompBwd cb;
+    cb.init(io, q, me.active, pl.n_feat);
     float S[32];  // step-sum of the gradient at the colour branch's input side (see the tile tail)
 #pragma unroll
     for (int j = 0; j < 32; ++j) S[j] = 0.f;
@@ -371,23 +356,7 @@ __global__ void __launch_bounds__(128, 1) lp_render_bwd_deep_kernel(LpRays R, Lp
       raw += F[I::FBL + 3]; lg0 += F[I::FBL]; lg1 += F[I::FBL + 1]; lg2 += F[I::FBL + 2];
       // ------------------------------ compositing gradient (as lp_render_bwd_tc_kernel) ------------------------------
       float g_raw, dl0, dl1, dl2;
-      {
-        if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-        nlt += delta * M.gain * lp_softplus(raw) * occ;
-        const float Tn = expf(-nlt);
-        const float w = T - Tn;
-        T = Tn;
-        const float s0 = lp_sigmoid(lg0), s1 = lp_sigmoid(lg1), s2 = lp_sigmoid(lg2);
-        const float p = fmaf(depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2]))) * occ;
-        prefix = fmaf(w, p, prefix);
-        const float suffix = (step == tot - 1) ? 0.f : total - prefix;
-        const float g_dop = Tn * p - suffix + g_nlt;
-        g_raw = g_dop * delta * M.gain * occ * lp_sigmoid(raw);
-        const float wo = w * occ;
-        dl0 = wo * gF[0] * s0 * (1.f - s0);
-        dl1 = wo * gF[1] * s1 * (1.f - s1);
-        dl2 = wo * gF[2] * s2 * (1.f - s2);
-      }
+      cb.grad(M, me.ray, step, step == tot - 1, raw, lg0, lg1, lg2, depth, delta, occ, g_raw, dl0, dl1, dl2);
       lp_tile8(tl, I::DYL, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
       bl0 += dl0; bl1 += dl1; bl2 += dl2; bl3 += g_raw;
       // ------------------------------ backward sweep ------------------------------

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256, 1) lp_render_fwd_tcw_kernel(LpRays R, LpM
       }
       lp_stage_row<HW, 32>(tme + WT_E, e);
     }
-    float nlt = 0.f, T = 1.f, acc_len = 0.f, acc_c[3] = {0.f, 0.f, 0.f};
+    LpCompFwd cf;
     float e_raw = 0.f, e_lg0 = 0.f, e_lg1 = 0.f, e_lg2 = 0.f;  // empty-space folding, see lp_render_fwd_tc_kernel
 
     for (int step = LP_TC_EMPTY_FOLD ? -1 : 0; step < tot; ++step) {
@@ -189,21 +189,12 @@ __global__ void __launch_bounds__(256, 1) lp_render_fwd_tcw_kernel(LpRays R, LpM
         raw = e_raw; lg0 = e_lg0; lg1 = e_lg1; lg2 = e_lg2;
       }
       // ---- compositing (renderer_fw.py:289-340) ----
-      if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-      nlt += SCAF ? delta * M.gain * lp_softplus(raw) * occ : delta * M.gain * lp_softplus(raw);
-      const float Tn = expf(-nlt);
-      const float w = T - Tn;
-      T = Tn;
-      acc_len = fmaf(w, depth, acc_len);
-      const float wc = SCAF ? w * occ : w;
-      acc_c[0] = fmaf(wc, lp_sigmoid(lg0), acc_c[0]);
-      acc_c[1] = fmaf(wc, lp_sigmoid(lg1), acc_c[1]);
-      acc_c[2] = fmaf(wc, lp_sigmoid(lg2), acc_c[2]);
+      cf.add(M, me.ray, step, raw, lg0, lg1, lg2, depth, delta, occ);
     }
     if (me.active) {
-      out_len[me.ray] = acc_len;
-      out_nlt[me.ray] = nlt;
-      for (int c = 0; c < D.n_feat; ++c) out_feat[(long long)me.ray * feat_stride + c] = acc_c[c];
+      out_len[me.ray] = cf.len;
+      out_nlt[me.ray] = cf.nlt;
+      for (int c = 0; c < D.n_feat; ++c) out_feat[(long long)me.ray * feat_stride + c] = c == 0 ? cf.c0 : (c == 1 ? cf.c1 : cf.c2);
     }
   }
 #undef LP_W_ROUND
@@ -398,14 +389,8 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tcw_kernel(LpRays R, LpM
       }
       lp_stage_row<W, 32>(tme + WB_E + pk, e);
     }
-    const float g_len = me.active ? io.g_len[q] : 0.f, g_nlt = me.active ? io.g_nlt[q] : 0.f;
-    float gF[3], total = g_len * io.len[q];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      gF[c] = (me.active && c < D.n_feat) ? io.g_feat[(long long)q * io.g_feat_stride + c] : 0.f;
-      if (c < D.n_feat) total = fmaf(gF[c], io.feat[(long long)q * io.feat_stride + c], total);
-    }
-    float nlt = 0.f, T = 1.f, prefix = 0.f;
+    LpCompBwd cb;
+    cb.init(io, q, me.active, D.n_feat);
     float S[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) S[j] = 0.f;
@@ -429,22 +414,7 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tcw_kernel(LpRays R, LpM
     bool any_empty = false;
 
     auto composite = [&](float raw, float lg0, float lg1, float lg2, int step, float& g_raw, float& dl0, float& dl1, float& dl2) {
-      if (M.noise) raw += M.sigma * lp_sample_noise(M, me.ray, step);
-      const float occ = SCAF ? cur.occ : 1.f;
-      nlt += cur.delta * M.gain * lp_softplus(raw) * occ;
-      const float Tn = expf(-nlt);
-      const float w = T - Tn;
-      T = Tn;
-      const float s0 = lp_sigmoid(lg0), s1 = lp_sigmoid(lg1), s2 = lp_sigmoid(lg2);
-      const float p = fmaf(cur.depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2]))) * occ;
-      prefix = fmaf(w, p, prefix);
-      const float suffix = (step == tot - 1) ? 0.f : total - prefix;
-      const float g_dop = Tn * p - suffix + g_nlt;
-      g_raw = g_dop * cur.delta * M.gain * occ * lp_sigmoid(raw);
-      const float wo = w * occ;
-      dl0 = wo * gF[0] * s0 * (1.f - s0);
-      dl1 = wo * gF[1] * s1 * (1.f - s1);
-      dl2 = wo * gF[2] * s2 * (1.f - s2);
+      cb.grad(M, me.ray, step, step == tot - 1, raw, lg0, lg1, lg2, cur.depth, cur.delta, SCAF ? cur.occ : 1.f, g_raw, dl0, dl1, dl2);
     };
 
     for (int step = LP_TC_EMPTY_FOLD ? -1 : 0; step < tot + (LP_TC_EMPTY_FOLD ? 1 : 0); ++step) {
