@@ -1,12 +1,13 @@
 // Renderer fast path for the default decoder shape (trunk/opacity/colour = 2/2/2 layers, hidden width
 // 32, C in {16,32} grid channels, <= 3 colour channels, no separate colour grid): the per-sample MLP
-// runs on the 5th-generation tensor cores (tcgen05) with one THREAD per sample.  Other decoder shapes
-// take the generic kernels of lp_render_generic.cuh.
+// runs on the 5th-generation tensor cores (tcgen05) with one THREAD per sample.  Variants of the same scheme:
+// lp_render_tc_cg.cuh (separate colour grid), lp_render_tc_wide.cuh (hidden width 64), lp_render_tc_deep.cuh (other
+// layer counts), lp_splat_tc.cuh (MLP splatter); everything else takes the generic kernels of lp_render_generic.cuh.
 //
 // A group of 128 threads marches 128 rays in lock step.  At every step each thread gathers the grid
 // features of its own sample into registers, splits them into two bf16 terms (x = hi + lo) and stores
-// them as its row of the A operand in tensor memory (tcgen05.st).  One elected thread then issues the
-// layer as M = 128 MMAs whose B operand (the weights, also hi + lo, built once per CTA) sits in shared
+// them as its row of the A operand in tensor memory (tcgen05.st).  Lane 0 of each of the group's warps then issues
+// its share of the layer's M = 128 MMAs whose B operand (the weights, also hi + lo, built once per CTA) sits in shared
 // memory; three products hi*Whi + lo*Whi + hi*Wlo give ~1e-5 relative accuracy with fp32 accumulation
 // (tools/tc_test3.cu).  The accumulator comes back with tcgen05.ld as one 32-wide row per thread, so
 // bias, ReLU, the next split and finally the 4-wide output layer and the compositing are plain
@@ -258,11 +259,7 @@ LP_DEVICE void lp_stage_row(unsigned taddr_a, const float (&x)[N]) {
 // per-group tensor-memory columns (forward): A hi 0..15 / lo 16..31, encoding hi 32..47 / lo 48..63, D 64..127
 constexpr int TC_A = 0, TC_E = 32, TC_D = 64, TC_GROUP_COLS = 128;
 
-// leader thread: D(n columns) = A(K) x W, three bf16 products per 16-wide k-step.
-// (One thread issues a tcgen05.mma every ~46 cycles while the pipe needs 16 for N = 32; dealing the
-// MMAs of a product to several issuing threads -- legal once the accumulator is pre-cleared so that all
-// of them accumulate -- reaches the pipe rate in isolation (tools/tc_test2.cu) but made the kernels
-// slower: 84.7 vs 75.9 ms backward.  The chain is not bound by MMA issue.)
+// single-issuer form (LP_TC_ISSUERS == 1 builds): D(n columns) = A(K) x W, three bf16 products per 16-wide k-step
 LP_DEVICE void lp_issue_layer(unsigned tbase, int d_col, int a_col, lp_kdesc_t whi, lp_kdesc_t wlo, int ksteps, int k0,
                               int nstride, int n, bool first, int lo_off = 16) {
 #pragma unroll
