@@ -156,21 +156,33 @@ __global__ void __launch_bounds__(256, 1) lp_render_fwd_deep_kernel(LpRays R, Lp
       lp_stage_row<32, 16>(tme + DT_E, e);
     }
     LpCompFwd cf;
-    for (int step = 0; step < tot; ++step) {
-      const Sched sc = lp_sched(step, M);
+    float e_raw = 0.f, e_lg0 = 0.f, e_lg1 = 0.f, e_lg2 = 0.f;  // empty-space folding, see lp_render_fwd_tc_kernel
+    for (int step = LP_TC_EMPTY_FOLD ? -1 : 0; step < tot; ++step) {
+      const bool probe = step < 0;
+      const Sched sc = lp_sched(probe ? 0 : step, M);
       float depth, delta;
       lp_depth_delta(sc, me.near, me.far, depth, delta);
       float occ = 1.f;
+      bool hit = false;
       {
-        float x = me.ox + depth * me.dx, y = me.oy + depth * me.dy, z = me.oz + depth * me.dz;
-        if (M.contract) lp_contract(x, y, z);
-        if (SCAF) {
-          occ = lp_nearest(SC, me.b, x, y, z);
-          if (!lp_bar_any(1 + grp, GT, occ != 0.f)) continue;
-        }
-        const float oob = M.mask_oob ? lp_in_bounds(x, y, z) : 1.f;
         float x0[C];
-        lp_gather_regs<C>(G, me.b, x, y, z, oob, x0);
+        if (!probe) {
+          float x = me.ox + depth * me.dx, y = me.oy + depth * me.dy, z = me.oz + depth * me.dz;
+          if (M.contract) lp_contract(x, y, z);
+          if (SCAF) {
+            occ = lp_nearest(SC, me.b, x, y, z);
+            if (!lp_bar_any(1 + grp, GT, occ != 0.f)) continue;
+          }
+          const float oob = M.mask_oob ? lp_in_bounds(x, y, z) : 1.f;
+          hit = lp_gather_regs<C>(G, me.b, x, y, z, oob, x0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) x0[c] = 0.f;
+        }
+        if (LP_TC_EMPTY_FOLD && !probe && !lp_bar_any(1 + grp, GT, hit)) {  // every sample of the group is empty
+          cf.add(M, me.ray, step, e_raw, e_lg0, e_lg1, e_lg2, depth, delta, occ);
+          continue;
+        }
         lp_stage_row<C, 16>(tme + DT_A, x0);
       }
       float v[32], trv[32];
@@ -199,6 +211,7 @@ __global__ void __launch_bounds__(256, 1) lp_render_fwd_deep_kernel(LpRays R, Lp
         dp_logits(F, e, lg0, lg1, lg2);
       }
       raw += F[I::FBL + 3]; lg0 += F[I::FBL]; lg1 += F[I::FBL + 1]; lg2 += F[I::FBL + 2];
+      if (probe) { e_raw = raw; e_lg0 = lg0; e_lg1 = lg1; e_lg2 = lg2; continue; }
       cf.add(M, me.ray, step, raw, lg0, lg1, lg2, depth, delta, occ);
     }
     if (me.active) {
@@ -306,14 +319,19 @@ __global__ void __launch_bounds__(128, 1) lp_render_bwd_deep_kernel(LpRays R, Lp
 #pragma unroll
     for (int j = 0; j < 32; ++j) S[j] = 0.f;
 
-    for (int step = 0; step < tot; ++step) {
-      const Sched sc = lp_sched(step, M);
+    // empty-space folding (see lp_render_bwd_tc_kernel): probe iteration, summed gradients of the empty steps, one fold iteration
+    float e_raw = 0.f, e_lg0 = 0.f, e_lg1 = 0.f, e_lg2 = 0.f, G_raw = 0.f, L0 = 0.f, L1 = 0.f, L2 = 0.f;
+    bool any_empty = false;
+    for (int step = LP_TC_EMPTY_FOLD ? -1 : 0; step < tot + (LP_TC_EMPTY_FOLD ? 1 : 0); ++step) {
+      const bool probe = step < 0, virt = step == tot, real = !probe && !virt;
+      if (virt && !any_empty) break;
+      const Sched sc = lp_sched(real ? step : 0, M);
       float depth, delta;
       lp_depth_delta(sc, me.near, me.far, depth, delta);
       float px = me.ox + depth * me.dx, py = me.oy + depth * me.dy, pz = me.oz + depth * me.dz;
       if (M.contract) lp_contract(px, py, pz);
       float occ = 1.f;
-      if (SCAF) {
+      if (SCAF && real) {
         occ = lp_nearest(SC, me.b, px, py, pz);
         if (!lp_bar_any(1, GT, occ != 0.f)) continue;
       }
@@ -322,7 +340,20 @@ __global__ void __launch_bounds__(128, 1) lp_render_bwd_deep_kernel(LpRays R, Lp
       float raw = 0.f, lg0 = 0.f, lg1 = 0.f, lg2 = 0.f;
       {
         float x0[C];
-        lp_gather_regs<C>(G, me.b, px, py, pz, oob, x0);
+        bool hit = false;
+        if (real) {
+          hit = lp_gather_regs<C>(G, me.b, px, py, pz, oob, x0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) x0[c] = 0.f;
+        }
+        if (LP_TC_EMPTY_FOLD && real && !lp_bar_any(1, GT, hit)) {  // every sample of the group is empty
+          float g_raw, dl0, dl1, dl2;
+          cb.grad(M, me.ray, step, step == tot - 1, e_raw, e_lg0, e_lg1, e_lg2, depth, delta, occ, g_raw, dl0, dl1, dl2);
+          G_raw += g_raw; L0 += dl0; L1 += dl1; L2 += dl2;
+          any_empty = true;
+          continue;
+        }
         if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);  // the previous step's dW products have consumed the tiles
         lp_tile_row<C>(tl, I::X0, s, x0);
         lp_stage_row<C, 16>(tme + DT_A, x0);
@@ -355,8 +386,10 @@ __global__ void __launch_bounds__(128, 1) lp_render_bwd_deep_kernel(LpRays R, Lp
       }
       raw += F[I::FBL + 3]; lg0 += F[I::FBL]; lg1 += F[I::FBL + 1]; lg2 += F[I::FBL + 2];
       // ------------------------------ compositing gradient (as lp_render_bwd_tc_kernel) ------------------------------
+      if (probe) { e_raw = raw; e_lg0 = lg0; e_lg1 = lg1; e_lg2 = lg2; continue; }
       float g_raw, dl0, dl1, dl2;
-      cb.grad(M, me.ray, step, step == tot - 1, raw, lg0, lg1, lg2, depth, delta, occ, g_raw, dl0, dl1, dl2);
+      if (!virt) cb.grad(M, me.ray, step, step == tot - 1, raw, lg0, lg1, lg2, depth, delta, occ, g_raw, dl0, dl1, dl2);
+      else { g_raw = G_raw; dl0 = L0; dl1 = L1; dl2 = L2; }
       lp_tile8(tl, I::DYL, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
       bl0 += dl0; bl1 += dl1; bl2 += dl2; bl3 += g_raw;
       // ------------------------------ backward sweep ------------------------------
@@ -446,7 +479,7 @@ __global__ void __launch_bounds__(128, 1) lp_render_bwd_deep_kernel(LpRays R, Lp
         lp_tmem_zero<C>(tme + DT_D);
 #pragma unroll
         for (int c = 0; c < C; ++c) d[c] *= oob;
-        if (me.active && oob != 0.f) lp_splat_regs<C>(G, io.g_grid, me.b, px, py, pz, d);
+        if (real && me.active && oob != 0.f) lp_splat_regs<C>(G, io.g_grid, me.b, px, py, pz, d);
       }
     }
     // ---- per-tile tail: encoding gradient and the encoding's share of the first colour layer's dW ----

@@ -117,3 +117,13 @@ def test_hostsim_renderer_layer_counts_tensor_core_path(lib, layers, C, sigma):
     for k, v in got.items():
         tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
         assert rel_err(v, want[k]) < tol, (layers, k, rel_err(v, want[k]))
+
+
+def test_hostsim_layer_counts_empty_space_folding(lib):
+    c = synthetic_case(n=160, C=16, hidden=32, layers=(3, 2, 3), color_grid=False)
+    c = coherent_case(c, n=160, pixel=0.01, seed=3, mask_oob=1, origin=(1.3, -0.2, -3.0), near=0.3, far=6.0)
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cpu")
+    for k, v in got.items():
+        tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
+        assert rel_err(v, want[k]) < tol, (k, rel_err(v, want[k]))
