@@ -85,6 +85,23 @@ LP_DEVICE void lp_depth_delta(const Sched& s, float near, float far, float& dept
   }
 }
 
+// ---- one tensor-core round trip of a group (shared by every kernel of the family) ----
+// HANDOFF: publish this thread's staged operand row (tcgen05.wait::st + fence), meet the group at named barrier BARID,
+// and let the issuing threads run ISSUE (which ends with their tcgen05.commit to the group's mbarrier);
+// WAIT: block until the result is in tensor memory.  Independent work may sit between the two.
+#define LP_TCG_HANDOFF(BARID, NTHREADS, ISSUER, ISSUE) \
+  lp_tmem_wait_st();                                   \
+  lp_tc_fence_before();                                \
+  lp_bar_sync(BARID, NTHREADS);                        \
+  if (ISSUER) {                                        \
+    lp_tc_fence_after();                               \
+    ISSUE;                                             \
+  }
+#define LP_TCG_WAIT(BAR, PHASE) \
+  lp_mbar_wait(BAR, PHASE);     \
+  PHASE ^= 1;                   \
+  lp_tc_fence_after();
+
 // ---- compositing of one sample, shared by every tensor-core renderer kernel ----
 // forward (renderer_fw.py:289-340): NLT += delta*gain*softplus(raw)*occ; w = T_prev - T; len += w*depth; feat += w*occ*sigmoid(logit)
 struct LpCompFwd {
@@ -806,18 +823,8 @@ __global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R,
 #define LP_TC_HANDOFF(ISSUE)
 #define LP_TC_WAIT()
 #else
-#define LP_TC_HANDOFF(ISSUE)               \
-  lp_tmem_wait_st();                       \
-  lp_tc_fence_before();                    \
-  lp_bar_sync(1 + grp, GTH);               \
-  if (leader) {                            \
-    lp_tc_fence_after();                   \
-    ISSUE;                                 \
-  }
-#define LP_TC_WAIT()                       \
-  lp_mbar_wait(bar, phase);                \
-  phase ^= 1;                              \
-  lp_tc_fence_after();
+#define LP_TC_HANDOFF(ISSUE) LP_TCG_HANDOFF(1 + grp, GTH, leader, ISSUE)
+#define LP_TC_WAIT() LP_TCG_WAIT(bar, phase)
 #endif
 #define LP_TC_ROUND(ISSUE) LP_TC_HANDOFF(ISSUE) LP_TC_WAIT()
 

@@ -240,17 +240,7 @@ __global__ void __launch_bounds__(384, 1) lp_render_bwd_cg_kernel(LpRays R, LpMa
   const int num_tiles = (R.n + GT - 1) / GT;
   const int tot = M.S + M.S_inf;
 
-#define LP_CG_ROUND(ISSUE)                 \
-  lp_tmem_wait_st();                       \
-  lp_tc_fence_before();                    \
-  lp_bar_sync(1 + grp, GT);                \
-  if (issuer) {                            \
-    lp_tc_fence_after();                   \
-    ISSUE;                                 \
-  }                                        \
-  lp_mbar_wait(bar, phase);                \
-  phase ^= 1;                              \
-  lp_tc_fence_after();
+#define LP_CG_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, issuer, ISSUE) LP_TCG_WAIT(bar, phase)
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
     const Ray1 me = lp_load_ray1(R, tile * GT + s, G.g[0].B);

@@ -98,18 +98,7 @@ LP_DEVICE void dp_load_enc(const LpRays& R, int q, float (&e)[32]) {
   }
 }
 
-#define LP_DP_ROUND(ISSUE)                 \
-  lp_tmem_wait_st();                       \
-  lp_tc_fence_before();                    \
-  lp_bar_sync(1 + grp, GT);                \
-  if (issuer) {                            \
-    lp_tc_fence_after();                   \
-    ISSUE;                                 \
-    lp_tc_commit(bar);                     \
-  }                                        \
-  lp_mbar_wait(bar, phase);                \
-  phase ^= 1;                              \
-  lp_tc_fence_after();
+#define LP_DP_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, issuer, ISSUE; lp_tc_commit(bar)) LP_TCG_WAIT(bar, phase)
 #define LP_DP_LD(v) lp_tmem_ld32u(tme + DT_D, v); lp_tmem_zero<32>(tme + DT_D)
 
 // ===========================================================================================

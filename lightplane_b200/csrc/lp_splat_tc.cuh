@@ -107,18 +107,7 @@ __global__ void __launch_bounds__(512, 1) lp_mlp_splat_fwd_tc_kernel(LpRays R, L
   const int num_tiles = (R.n + GT - 1) / GT;
   const int tot = M.S + M.S_inf;
 
-#define LP_SP_ROUND(ISSUE)                 \
-  lp_tmem_wait_st();                       \
-  lp_tc_fence_before();                    \
-  lp_bar_sync(1 + grp, GT);                \
-  if (issuer) {                            \
-    lp_tc_fence_after();                   \
-    ISSUE;                                 \
-    lp_tc_commit(bar);                     \
-  }                                        \
-  lp_mbar_wait(bar, phase);                \
-  phase ^= 1;                              \
-  lp_tc_fence_after();
+#define LP_SP_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, issuer, ISSUE; lp_tc_commit(bar)) LP_TCG_WAIT(bar, phase)
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
     const Ray1 me = lp_load_ray1(R, tile * GT + (tid % GT), OUT.g[0].B);
@@ -235,17 +224,7 @@ __global__ void __launch_bounds__(512, 1) lp_mlp_splat_bwd_tc_kernel(LpRays R, L
   const int num_tiles = (R.n + GT - 1) / GT;
   const int tot = M.S + M.S_inf;
 
-#define LP_SP_ROUND(ISSUE)                 \
-  lp_tmem_wait_st();                       \
-  lp_tc_fence_before();                    \
-  lp_bar_sync(1 + grp, GT);                \
-  if (issuer) {                            \
-    lp_tc_fence_after();                   \
-    ISSUE;                                 \
-  }                                        \
-  lp_mbar_wait(bar, phase);                \
-  phase ^= 1;                              \
-  lp_tc_fence_after();
+#define LP_SP_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, issuer, ISSUE) LP_TCG_WAIT(bar, phase)
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
     const Ray1 me = lp_load_ray1(R, tile * GT + s, GG.g[0].B);
