@@ -22,6 +22,9 @@
 
 #include "lp_render_generic.cuh"
 
+#ifndef LP_TC_FWD_GROUPS
+#define LP_TC_FWD_GROUPS 4  // groups of 128 threads per CTA in the forward kernel (TMEM: 128 columns each)
+#endif
 #ifndef LP_TC_EMPTY_FOLD
 #define LP_TC_EMPTY_FOLD 1  // reuse the decoder's zero-feature output at steps where a whole group is in empty space
 #endif
@@ -346,7 +349,7 @@ LP_DEVICE bool lp_gather_regs(const LpGridSet& G, int b, float x, float y, float
 // forward
 // ===========================================================================================
 template <int C, bool SCAF>
-__global__ void __launch_bounds__(512, 1) lp_render_fwd_tc_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
+__global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
                                                                    LpGridSet SC,
                                                                    const float* __restrict__ params,
                                                                    float* __restrict__ out_len, float* __restrict__ out_nlt,
@@ -540,7 +543,7 @@ static inline int lp_tc_num_sms() {
 template <int C, bool SCAF>
 static int lp_tc_render_forward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, float* out_len, float* out_nlt,
                                   float* out_feat, int feat_stride) {
-  const int groups = 4;
+  const int groups = LP_TC_FWD_GROUPS;
   const size_t bytes = Img<C>::FWD_END + 128;
   if (LP_TC_SET_SMEM((lp_render_fwd_tc_kernel<C, SCAF>), bytes)) return LP_ERR_CUDA;
   const int tiles = (a.R.n + GT - 1) / GT;
