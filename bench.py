@@ -192,6 +192,8 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tile-walk", dest="tile_walk", action="store_false",
+                    help="do not pass the image width (ray_image_width): rays are walked as 128-ray scan-line runs")
     # non-default workloads (e.g. BASELINE.json configs[4]: --samples 256 --plane 128 --grid-chn 32)
     ap.add_argument("--samples", type=int, default=S)
     ap.add_argument("--plane", type=int, default=PLANE)
@@ -241,7 +243,7 @@ def main():
         for p in params:
             p.grad = None
         rays = lp.Rays(directions=rays_t[0], origins=rays_t[1], grid_idx=rays_t[2], near=rays_t[3], far=rays_t[4])
-        _, _, feat = model(rays, grids)
+        _, _, feat = model(rays, grids, ray_image_width=args.width if args.tile_walk else None)
         loss = ((feat - tgt) ** 2).mean()
         loss.backward()
         if world > 1:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 1
+#define LP_ABI_VERSION 2
 #define LP_MAX_GRIDS 8   /* grids per grid-list */
 #define LP_MAX_LAYERS 8  /* layers per MLP */
 
@@ -71,6 +71,11 @@ typedef struct lp_march_cfg {
   int32_t noise_seed;
   int32_t noise_num_rays;     /* ray count used for the 2nd hash index: N rounded up to 16,
                                  as the reference pads rays (renderer_fw.py:290-294)              */
+  int32_t ray_image_width;    /* scheduling hint, 0 = none: the N rays are a row-major image of this
+                                 width (multiple of 16, N a multiple of 8 rows); the tensor-core
+                                 kernels then walk 16x8-pixel tiles instead of 128-ray scan-line runs
+                                 (texel-coherent gathers / reductions).  Results do not depend on it
+                                 beyond floating-point summation order.                            */
 } lp_march_cfg;
 
 /* Decoder layout inside the flat `mlp_params` vector (reference: mlp_utils.py:390-456 and

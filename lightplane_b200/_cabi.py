@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 LP_MAX_GRIDS = 8
-LP_ABI_VERSION = 1
+LP_ABI_VERSION = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB_PATH = os.path.join(_HERE, "csrc", "liblightplane_b200.so")
@@ -57,6 +57,7 @@ class MarchCfg(C.Structure):
         ("noise_sigma", C.c_float),
         ("noise_seed", C.c_int32),
         ("noise_num_rays", C.c_int32),
+        ("ray_image_width", C.c_int32),
     ]
 
 
@@ -202,6 +203,7 @@ def make_cfg(
     noise_sigma=0.0,
     noise_seed=0,
     num_rays=0,
+    ray_image_width=0,
 ) -> MarchCfg:
     c = MarchCfg()
     c.num_samples, c.num_samples_inf = int(num_samples), int(num_samples_inf)
@@ -213,6 +215,7 @@ def make_cfg(
     seed = int(noise_seed) & 0xFFFFFFFF
     c.noise_seed = seed - (1 << 32) if seed >= (1 << 31) else seed
     c.noise_num_rays = ((int(num_rays) + 15) // 16) * 16
+    c.ray_image_width = int(ray_image_width or 0)
     return c
 
 

@@ -8,6 +8,7 @@
 #include "lp_render_generic.cuh"
 #include "lp_splat.cuh"
 #include "lp_render_tc.cuh"
+#include "lp_render_tc_bwd.cuh"
 #include "lp_render_tc_cg.cuh"
 #include "lp_splat_tc.cuh"
 #include "lp_render_tc_wide.cuh"
@@ -93,6 +94,7 @@ static int lp_make_march(const lp_march_cfg* c, LpMarch* m) {
   m->mask_oob = c->mask_out_of_bounds != 0; m->contract = c->contract_coords != 0;
   m->noise = c->inject_noise != 0 && c->noise_sigma > 0.f;
   m->sigma = c->noise_sigma; m->seed = c->noise_seed; m->noise_num_rays = c->noise_num_rays;
+  m->img_w = c->ray_image_width > 0 ? c->ray_image_width : 0;  // validated against the ray count by the renderer entry points
   return LP_OK;
 }
 
@@ -202,6 +204,8 @@ static int lp_render_common(const lp_march_cfg* cfg, const lp_decoder_spec* spec
   if ((rc = lp_make_gridset(scaffold, &a->SC, "scaffold"))) return rc;
   if ((rc = lp_make_decoder(spec, a->G.C, &a->D, &a->A))) return rc;
   if ((rc = lp_make_rays(rays, &a->R, a->D.in_c))) return rc;
+  // the tile walk is a hint: it applies only when the rays really are whole 16x8-pixel tiles of an image that wide
+  if (a->M.img_w % 16 != 0 || a->R.n % (a->M.img_w > 0 ? a->M.img_w * 8 : 1) != 0) a->M.img_w = 0;
   if (a->D.use_color_grid) {
     if (!color_grid) LP_FAIL(LP_ERR_INVALID_ARG, "n_layers_trunk == 0 requires a color_grid");
     if (a->CG.C != a->G.C) LP_FAIL(LP_ERR_INVALID_ARG, "color_grid channels != grid channels");

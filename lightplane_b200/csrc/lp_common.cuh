@@ -44,6 +44,7 @@ struct LpMarch {
   int noise;
   float sigma;
   int seed, noise_num_rays;
+  int img_w;  // > 0: rays form a row-major image of this width, walked in 16x8-pixel tiles (validated on the host)
 };
 
 // One dense layer inside the flat parameter vector.

@@ -82,6 +82,56 @@ LP_DEVICE unsigned lp_pack_bf16x2(float lo, float hi) {  // lo -> bits 0..15, hi
 #endif
 }
 
+// fp32 -> tf32 (10-bit mantissa) with round-to-nearest, as a 32-bit pattern; the tensor core ignores the low 13 bits
+// of a kind::tf32 operand, so feeding raw fp32 would truncate (a systematic bias of -2^-12 per factor)
+LP_DEVICE unsigned lp_tf32_rna(float x) {
+#if defined(LP_HOSTSIM)
+  unsigned u = __float_as_uint(x);
+  if ((u & 0x7f800000u) == 0x7f800000u) return u;
+  return (u + 0x1000u) & 0xffffe000u;
+#else
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+#endif
+}
+// ReLU gate from a packed pair of bf16 activations: a (b) survives iff the low (high) half of w is non-zero
+LP_DEVICE void lp_gate2(unsigned w, float& a, float& b) {
+#if defined(LP_HOSTSIM)
+  if (!(w & 0x7fffu)) a = 0.f;
+  if (!((w >> 16) & 0x7fffu)) b = 0.f;
+#else
+  asm("{\n\t.reg .pred p, q;\n\tsetp.ne.bf16x2 p|q, %2, %3;\n\tselp.f32 %0, %0, 0f00000000, p;\n\t"
+      "selp.f32 %1, %1, 0f00000000, q;\n\t}\n" : "+f"(a), "+f"(b) : "r"(w), "r"(0u));
+#endif
+}
+// approximate transcendentals of the tensor-core kernels' compositing (ex2.approx / lg2.approx / rcp.approx, relative
+// error ~2^-22): the forward kernel and the backward kernel's recompute use the same ones, so the saved outputs and
+// the recomputed prefix sums stay consistent
+LP_DEVICE float lp_fast_exp(float x) {
+#if defined(LP_HOSTSIM)
+  return expf(x);
+#else
+  return __expf(x);
+#endif
+}
+LP_DEVICE float lp_fast_rcp(float x) {
+#if defined(LP_HOSTSIM)
+  return 1.f / x;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+LP_DEVICE float lp_fast_log(float x) {
+#if defined(LP_HOSTSIM)
+  return logf(x);
+#else
+  return __logf(x);
+#endif
+}
+
 #if !defined(LP_HOSTSIM)
 LP_DEVICE unsigned lp_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -98,6 +148,10 @@ LP_DEVICE void lp_mbar_wait(unsigned long long* bar, int parity) {
         : "r"(lp_smem_u32(bar)), "r"(parity)
         : "memory");
   }
+}
+// plain arrival of one thread (release semantics at CTA scope)
+LP_DEVICE void lp_mbar_arrive(unsigned long long* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(lp_smem_u32(bar)) : "memory");
 }
 LP_DEVICE void lp_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 LP_DEVICE void lp_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

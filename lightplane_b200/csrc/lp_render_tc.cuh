@@ -107,19 +107,54 @@ LP_DEVICE void lp_depth_delta(const Sched& s, float near, float far, float& dept
 
 // ---- compositing of one sample, shared by every tensor-core renderer kernel ----
 // forward (renderer_fw.py:289-340): NLT += delta*gain*softplus(raw)*occ; w = T_prev - T; len += w*depth; feat += w*occ*sigmoid(logit)
+// Transcendentals of the compositing: ex2/lg2/rcp.approx forms (relative error ~2^-22, lp_platform.cuh).  The forward
+// kernel and the backward kernel's recompute share them, so saved outputs and recomputed prefix sums stay consistent.
+#ifndef LP_TC_FAST_MATH
+#define LP_TC_FAST_MATH 1
+#endif
+// softplus(x) and its derivative sigmoid(x) from one exponential; log1p(e) = log(u) * e / (u - 1), u = 1 + e, keeps
+// the relative accuracy for small e (func_util.py:19-28)
+LP_DEVICE void lp_softplus_sig(float x, float& sp, float& sg) {
+#if LP_TC_FAST_MATH
+  const float e = lp_fast_exp(-fabsf(x));
+  const float u = 1.f + e, d = u - 1.f, r = lp_fast_rcp(u);
+  const float l1p = d == 0.f ? e : lp_fast_log(u) * e * lp_fast_rcp(d);
+  sp = fmaxf(x, 0.f) + l1p;
+  sg = x >= 0.f ? r : e * r;
+#else
+  sp = lp_softplus(x);
+  sg = lp_sigmoid(x);
+#endif
+}
+LP_DEVICE float lp_sig(float x) {
+#if LP_TC_FAST_MATH
+  return lp_fast_rcp(1.f + lp_fast_exp(-x));
+#else
+  return lp_sigmoid(x);
+#endif
+}
+LP_DEVICE float lp_expneg(float x) {  // exp(-x)
+#if LP_TC_FAST_MATH
+  return lp_fast_exp(-x);
+#else
+  return expf(-x);
+#endif
+}
 struct LpCompFwd {
   float nlt = 0.f, T = 1.f, len = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
   LP_DEVICE void add(const LpMarch& M, int ray, int step, float raw, float lg0, float lg1, float lg2, float depth, float delta, float occ) {
     if (M.noise) raw += M.sigma * lp_sample_noise(M, ray, step);
-    nlt += delta * M.gain * lp_softplus(raw) * occ;
-    const float Tn = expf(-nlt);
+    float sp, sg;
+    lp_softplus_sig(raw, sp, sg);
+    nlt += delta * M.gain * sp * occ;
+    const float Tn = lp_expneg(nlt);
     const float w = T - Tn;
     T = Tn;
     len = fmaf(w, depth, len);
     const float wc = w * occ;
-    c0 = fmaf(wc, lp_sigmoid(lg0), c0);
-    c1 = fmaf(wc, lp_sigmoid(lg1), c1);
-    c2 = fmaf(wc, lp_sigmoid(lg2), c2);
+    c0 = fmaf(wc, lp_sig(lg0), c0);
+    c1 = fmaf(wc, lp_sig(lg1), c1);
+    c2 = fmaf(wc, lp_sig(lg2), c2);
   }
 };
 // backward (renderer_bw.py:300-420), marching FORWARD with the saved outputs: with p_j = depth_j g_len + sum_c sigmoid_c gF_c,
@@ -143,16 +178,18 @@ struct LpCompBwd {
   LP_DEVICE void grad(const LpMarch& M, int ray, int step, bool last, float raw, float lg0, float lg1, float lg2, float depth, float delta,
                       float occ, float& g_raw, float& dl0, float& dl1, float& dl2) {
     if (M.noise) raw += M.sigma * lp_sample_noise(M, ray, step);
-    nlt += delta * M.gain * lp_softplus(raw) * occ;
-    const float Tn = expf(-nlt);
+    float sp, sg;
+    lp_softplus_sig(raw, sp, sg);
+    nlt += delta * M.gain * sp * occ;
+    const float Tn = lp_expneg(nlt);
     const float w = T - Tn;
     T = Tn;
-    const float s0 = lp_sigmoid(lg0), s1 = lp_sigmoid(lg1), s2 = lp_sigmoid(lg2);
+    const float s0 = lp_sig(lg0), s1 = lp_sig(lg1), s2 = lp_sig(lg2);
     const float p = fmaf(depth, g_len, fmaf(s0, gF[0], fmaf(s1, gF[1], s2 * gF[2]))) * occ;
     prefix = fmaf(w, p, prefix);
     const float suffix = last ? 0.f : total - prefix;
     const float g_dop = Tn * p - suffix + g_nlt;
-    g_raw = g_dop * delta * M.gain * occ * lp_sigmoid(raw);
+    g_raw = g_dop * delta * M.gain * occ * sg;
     const float wo = w * occ;
     dl0 = wo * gF[0] * s0 * (1.f - s0);
     dl1 = wo * gF[1] * s1 * (1.f - s1);
@@ -179,6 +216,8 @@ LP_DEVICE int lp_taps_i32(const LpGrid& g, int C, int b, float x, float y, float
     int x0, y0, z0, cx[2], cy[2], cz[2];
     float fx, fy, fz, wx[2], wy[2], wz[2];
     lp_axis_i(x, g.W, x0, fx); lp_axis_i(y, g.H, y0, fy); lp_axis_i(z, g.D, z0, fz);
+    if ((unsigned)(x0 + 1) > (unsigned)g.W || (unsigned)(y0 + 1) > (unsigned)g.H || (unsigned)(z0 + 1) > (unsigned)g.D)
+      return 0;  // no corner inside the grid: every tap weight is zero
     lp_corner_i(x0, fx, g.W, wx[0], wx[1], cx[0], cx[1]);
     lp_corner_i(y0, fy, g.H, wy[0], wy[1], cy[0], cy[1]);
     lp_corner_i(z0, fz, g.D, wz[0], wz[1], cz[0], cz[1]);
@@ -198,6 +237,7 @@ LP_DEVICE int lp_taps_i32(const LpGrid& g, int C, int b, float x, float y, float
   int u0, v0, cu[2], cv[2];
   float fu, fv, wu[2], wv[2];
   lp_axis_i(u, U, u0, fu); lp_axis_i(v, V, v0, fv);
+  if ((unsigned)(u0 + 1) > (unsigned)U || (unsigned)(v0 + 1) > (unsigned)V) return 0;  // the sample misses this plane
   lp_corner_i(u0, fu, U, wu[0], wu[1], cu[0], cu[1]);
   lp_corner_i(v0, fv, V, wv[0], wv[1], cv[0], cv[1]);
   const int bbase = (int)g.base + b * U * V * C;
@@ -210,6 +250,16 @@ LP_DEVICE int lp_taps_i32(const LpGrid& g, int C, int b, float x, float y, float
 }
 
 constexpr int GT = 128;  // threads = rays per group (the MMA's M)
+
+// Ray handled by thread s of ray tile `tile`.  Default: 128 consecutive rays.  With the image-width hint
+// (lp_march_cfg.ray_image_width) a tile is a 16x8-pixel block and a warp an 8x4 block of it, so that the samples a
+// warp gathers / scatters at one step share texels (fewer distinct L1/L2 lines per request, fewer conflicting reductions).
+LP_DEVICE int lp_tile_ray(const LpMarch& M, int tile, int s) {
+  if (M.img_w <= 0) return tile * GT + s;
+  const int tpr = M.img_w >> 4, ty = tile / tpr, tx = tile - ty * tpr;
+  const int w = s >> 5, l = s & 31;
+  return (ty * 8 + (w >> 1) * 4 + (l >> 3)) * M.img_w + tx * 16 + (w & 1) * 8 + (l & 7);
+}
 
 // ---- shared-memory weight image (byte offsets).  bf16 tiles are K-major UMMA operands
 // [n/8][k/8][8 n][8 k]; element (n, k) at ((n/8)*(K/8) + k/8)*128 + (n%8)*16 + (k%8)*2 ----
@@ -322,11 +372,7 @@ LP_DEVICE bool lp_gather_regs(const LpGridSet& G, int b, float x, float y, float
     int off[8];
     float w[8];
     const int nt = lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
-    float wsum = 0.f;
-#pragma unroll
-    for (int tp = 0; tp < 8; ++tp)
-      if (tp < nt) wsum += w[tp];
-    if (wsum == 0.f) continue;  // the sample misses this grid entirely
+    if (nt == 0) continue;  // the sample misses this grid entirely
     hit = true;
 #pragma unroll
     for (int tp = 0; tp < 8; ++tp) {
@@ -385,7 +431,7 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
   const int tot = M.S + M.S_inf;
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
-    const Ray1 me = lp_load_ray1(R, tile * GT + (tid % GT), G.g[0].B);
+    const Ray1 me = lp_load_ray1(R, lp_tile_ray(M, tile, tid % GT), G.g[0].B);
     {  // stage the ray encoding once (columns TC_E..): A operand of the colour layer's second half
       float e[32];
       const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)(me.active ? me.ray : R.n - 1) * H);
@@ -565,54 +611,8 @@ static inline int lp_tc_render_forward(cudaStream_t st, const LpRenderArgs& a, c
 
 
 // ===========================================================================================
-// backward
+// backward: helpers shared by every tensor-core backward kernel (the default-shape kernel itself is lp_render_tc_bwd.cuh)
 // ===========================================================================================
-// Shared memory after the forward image: the transposed weights of the three input-gradient products
-// (same K-major hi/lo form), then per group the bf16 operand tiles of the parameter-gradient GEMMs
-//     dW = A^T dY  over the group's 128 samples (the MMA's K),
-// all MN-major: element (row, sample s) at (row/8)*2048 + (s/8)*128 + (s%8)*16 + (row%8)*2, so a thread
-// writes 8 features of its sample as one 16-byte store.
-//   A1 = [h1 | trunk out | x0 | ones]   (rows 0-31, 32-63, 64..64+C, 64+C)       x  DY = [d_t | d_ho | d_hc | d_h1] (N = 128)
-//   A2 = [opacity hidden | colour hidden | ones]                                  x  DYL = [dlogit_0..2, g_raw, 0...] (N = 16)
-template <int C>
-struct BImg {
-  using I = Img<C>;
-  static constexpr int XT_HI = (I::FWD_END + 127) / 128 * 128;  // d_t:  [32 trunk][64: opacity hidden | colour hidden]
-  static constexpr int XT_LO = XT_HI + 4096;
-  static constexpr int XH_HI = XT_LO + 4096;                    // d_h1: [32][32]
-  static constexpr int XH_LO = XH_HI + 2048;
-  static constexpr int X0_HI = XH_LO + 2048;                    // d_x0: [C][32]
-  static constexpr int X0_LO = X0_HI + C * 64;
-  static constexpr int BARS = X0_LO + C * 64;                   // mbarriers + TMEM slot (128 B)
-  static constexpr int GROUPS = BARS + 128;
-  // per-group tiles
-  static constexpr int ONES1 = 8 + C / 8;                       // chunk of A1 whose first row is all ones
-  static constexpr int A1 = 0;
-  static constexpr int A2 = A1 + (ONES1 + 1) * 2048;
-  static constexpr int DY = A2 + 9 * 2048;
-  static constexpr int DYL = DY + 16 * 2048;
-  static constexpr int XCH = DYL + 2 * 2048;     // float4 [2][128]: partial output-layer sums of the two threads of a sample
-  static constexpr int GROUP_BYTES = XCH + 4096;
-  static_assert(A2 + 16 * 2048 <= GROUP_BYTES, "operand window leaves the group's region");
-};
-// tensor-memory columns: per group A (hi 0..31, lo 32..63), encoding (hi 64..79, lo 80..95), D 96..159;
-// shared by the CTA: the parameter-gradient accumulators
-constexpr int BT_A = 0, BT_E = 64, BT_D = 96, BT_GROUP_COLS = 160;
-constexpr int BT_W = 320, BT_L = 448, BT_ENC = 464;
-
-template <int C>
-LP_DEVICE void lp_build_bimg(unsigned char* sm, const float* __restrict__ P, const LpDecoder& D) {
-  using B = BImg<C>;
-  const LpLayer &t0 = D.trunk.l[0], &t1 = D.trunk.l[1], &o0 = D.opacity.l[0], &c0 = D.color.l[0];
-  const int tid = threadIdx.x, nth = blockDim.x;
-  for (int e = tid; e < 32 * 64; e += nth) {  // B[n = trunk feature][k]: k < 32 opacity hidden k, else colour hidden k-32
-    const int n = e >> 6, k = e & 63;
-    lp_put_w(sm, B::XT_HI, B::XT_LO, n, k, 64, k < 32 ? P[o0.w_off + n * o0.N + k] : P[c0.w_off + n * c0.N + (k - 32)]);
-  }
-  for (int e = tid; e < 32 * 32; e += nth) lp_put_w(sm, B::XH_HI, B::XH_LO, e >> 5, e & 31, 32, P[t1.w_off + (e >> 5) * t1.N + (e & 31)]);
-  for (int e = tid; e < C * 32; e += nth) lp_put_w(sm, B::X0_HI, B::X0_LO, e >> 5, e & 31, 32, P[t0.w_off + (e >> 5) * t0.N + (e & 31)]);
-}
-
 // this thread's sample s: features 8*chunk .. 8*chunk+7 of a tile
 LP_DEVICE void lp_tile8(unsigned char* tile, int chunk, int s, float x0, float x1, float x2, float x3, float x4, float x5,
                         float x6, float x7) {
@@ -645,56 +645,8 @@ LP_DEVICE void lp_gate_row(float (&x)[N], const unsigned char* tile, int chunk0,
     const uint4 w = *reinterpret_cast<const uint4*>(tile + (chunk0 + c) * 2048 + (s >> 3) * 128 + (s & 7) * 16);
     const unsigned ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (!(ww[e] & 0xffffu)) x[8 * c + 2 * e] = 0.f;
-      if (!(ww[e] >> 16)) x[8 * c + 2 * e + 1] = 0.f;
-    }
+    for (int e = 0; e < 4; ++e) lp_gate2(ww[e], x[8 * c + 2 * e], x[8 * c + 2 * e + 1]);
   }
-}
-
-// leader: the group's parameter-gradient products over its 128 samples (8 k-steps of 16)
-template <int C>
-LP_DEVICE void lp_issue_dw(unsigned tmem, unsigned char* gs, int accumulate) {
-  using B = BImg<C>;
-  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), a2 = lp_tc_mndesc_lo(gs + B::A2), dy = lp_tc_mndesc_lo(gs + B::DY),
-                   dyl = lp_tc_mndesc_lo(gs + B::DYL);
-#pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
-    lp_tc_mma_ss_mn(tmem + BT_W, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 128, accumulate | (ks > 0));
-    lp_tc_mma_ss_mn(tmem + BT_L, lp_tc_kadv(a2, ks * 256), lp_tc_kadv(dyl, ks * 256), 2048, 16, accumulate | (ks > 0));
-  }
-}
-// encoding^T x (step-sum of the colour-hidden gradient): A1 chunks 0-3 hold the encodings, DY chunks 8-11 the sums
-// issuer wi of 4: k-steps 2wi, 2wi+1 of both products
-template <int C>
-LP_DEVICE void lp_issue_dw_part(unsigned tmem, unsigned char* gs, int wi) {
-  using B = BImg<C>;
-  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), a2 = lp_tc_mndesc_lo(gs + B::A2), dy = lp_tc_mndesc_lo(gs + B::DY),
-                   dyl = lp_tc_mndesc_lo(gs + B::DYL);
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int ks = 2 * wi + j;
-    lp_tc_mma_ss_mn(tmem + BT_W, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 128, 1);
-    lp_tc_mma_ss_mn(tmem + BT_L, lp_tc_kadv(a2, ks * 256), lp_tc_kadv(dyl, ks * 256), 2048, 16, 1);
-  }
-}
-template <int C>
-LP_DEVICE void lp_issue_encw_part(unsigned tmem, unsigned char* gs, int wi) {
-  using B = BImg<C>;
-  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), dy = lp_tc_mndesc_lo(gs + B::DY + 8 * 2048);
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int ks = 2 * wi + j;
-    lp_tc_mma_ss_mn(tmem + BT_ENC, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 32, 1);
-  }
-}
-template <int C>
-LP_DEVICE void lp_issue_encw(unsigned tmem, unsigned char* gs, int accumulate) {
-  using B = BImg<C>;
-  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), dy = lp_tc_mndesc_lo(gs + B::DY + 8 * 2048);
-#pragma unroll
-  for (int ks = 0; ks < 8; ++ks)
-    lp_tc_mma_ss_mn(tmem + BT_ENC, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 32, accumulate | (ks > 0));
 }
 
 // adjoint of lp_gather_regs: the owner thread scatters its row into the grid gradient
@@ -708,11 +660,7 @@ LP_DEVICE void lp_splat_regs(const LpGridSet& G, float* grad, int b, float x, fl
     int off[8];
     float w[8];
     const int nt = lp_taps_i32(G.g[gi], C, b, x, y, z, off, w);
-    float wsum = 0.f;
-#pragma unroll
-    for (int tp = 0; tp < 8; ++tp)
-      if (tp < nt) wsum += w[tp];
-    if (wsum == 0.f) continue;
+    if (nt == 0) continue;
 #pragma unroll
     for (int tp = 0; tp < 8; ++tp) {
       if (tp < nt) {
@@ -726,424 +674,5 @@ LP_DEVICE void lp_splat_regs(const LpGridSet& G, float* grad, int b, float x, fl
   }
 }
 
-#ifndef LP_TC_ISSUERS
-#define LP_TC_ISSUERS 4  // MMA-issuing threads per group in the backward kernel (1 or 4)
-#endif
-#ifdef LP_ABL_NO_DW
-#define LP_ABL_DW(x)
-#else
-#define LP_ABL_DW(x) x
-#endif
-// NP threads per sample: thread part h of sample s owns columns [W*h, W*h + W) of every 32-wide
-// activation / gradient row (W = 32/NP) and channels [CW*h, ..) of the grid features (CW = C/NP); both
-// parts address the same TMEM lane (warps w and w+4 of a group share a lane quarter).  NP = 2 halves the
-// per-thread work and registers, doubling the warps that hide the tensor-core round trips, at the
-// price of duplicated ray/tap/compositing arithmetic and one exchange of the output layer's partial sums.
-template <int C, int NP, bool SCAF>
-__global__ void __launch_bounds__(256 * NP, 1) lp_render_bwd_tc_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G,
-                                                                        LpGridSet SC,
-                                                                        const float* __restrict__ params, LpBwdIo io) {
-  using I = Img<C>;
-  using B = BImg<C>;
-  constexpr int W = 32 / NP, CW = C / NP, GTH = GT * NP;
-  LP_DYN_SMEM(unsigned char, sm);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = tid / GTH, ngroups = blockDim.x / GTH, tg = tid % GTH;
-  const int s = tg % GT, h = tg / GT, wig = (tg >> 5) & 3;  // sample row, column part, TMEM lane quarter
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + B::BARS);  // [2g] round trips, [2g+1] dW; [8] init
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 10);
-  unsigned char* gs = sm + B::GROUPS + grp * B::GROUP_BYTES;
-  lp_build_img<C>(sm, params, D);
-  lp_build_bimg<C>(sm, params, D);
-  for (int e = tg; e < B::GROUP_BYTES / 16; e += GTH) reinterpret_cast<uint4*>(gs)[e] = make_uint4(0u, 0u, 0u, 0u);
-  __syncthreads();
-  if (h == 0) {  // rows of ones (bf16 1.0): first row of A1 chunk ONES1 and of A2 chunk 8
-    *reinterpret_cast<unsigned short*>(gs + B::A1 + B::ONES1 * 2048 + (s >> 3) * 128 + (s & 7) * 16) = 0x3F80;
-    *reinterpret_cast<unsigned short*>(gs + B::A2 + 8 * 2048 + (s >> 3) * 128 + (s & 7) * 16) = 0x3F80;
-  }
-  if (tid == 0) {
-    for (int i = 0; i < 8; ++i) lp_mbar_init(bars + i, LP_TC_ISSUERS);
-    lp_mbar_init(bars + 8, 1);
-    lp_mbar_init_fence();
-  }
-  if (tid < 32) lp_tmem_alloc512(tmem_slot);
-  lp_fence_async_smem();
-  lp_tc_fence_before();
-  __syncthreads();
-  lp_tc_fence_after();
-  const unsigned tmem = *tmem_slot;
-  if (tid == 0) {  // zero the accumulators: products of the (all-zero) gradient tiles with accumulate off
-    lp_issue_dw<C>(tmem, gs, 0);
-    lp_issue_encw<C>(tmem, gs, 0);
-    lp_tc_commit(bars + 8);
-  }
-  lp_mbar_wait(bars + 8, 0);
-  lp_tc_fence_after();
-  __syncthreads();
-
-  const unsigned tbase = tmem + (unsigned)(grp * BT_GROUP_COLS);
-  const unsigned tme = lp_taddr(tbase, wig, 0);
-#if LP_TC_ISSUERS == 4
-  const bool leader = lane == 0 && tg < 128;  // four issuing threads per group, see lp_issue_layer_part
-  const int wi = tg >> 5;
-#else
-  const bool leader = tg == 0;
-#endif
-  const float* F = reinterpret_cast<const float*>(sm + I::F32);
-  float4* xch = reinterpret_cast<float4*>(gs + B::XCH);
-  const int pk = (W / 2) * h, fc = W * h, ck = (W / 8) * h;  // packed-column / fp32-column / tile-chunk offset of this part
-#if LP_TC_ISSUERS == 4
-  lp_tmem_zero<W>(tme + BT_D + fc);
-  lp_tmem_zero<W>(tme + BT_D + 32 + fc);
-#define LP_TC_ZERO(n, addr) lp_tmem_zero<n>(addr)
-#else
-#define LP_TC_ZERO(n, addr)
-#endif
-  const lp_kdesc_t w_t0h = lp_tc_kdesc_lo(sm + I::T0_HI), w_t0l = lp_tc_kdesc_lo(sm + I::T0_LO),
-                   w_t1h = lp_tc_kdesc_lo(sm + I::T1_HI), w_t1l = lp_tc_kdesc_lo(sm + I::T1_LO),
-                   w_och = lp_tc_kdesc_lo(sm + I::OC_HI), w_ocl = lp_tc_kdesc_lo(sm + I::OC_LO),
-                   w_xth = lp_tc_kdesc_lo(sm + B::XT_HI), w_xtl = lp_tc_kdesc_lo(sm + B::XT_LO),
-                   w_xhh = lp_tc_kdesc_lo(sm + B::XH_HI), w_xhl = lp_tc_kdesc_lo(sm + B::XH_LO),
-                   w_x0h = lp_tc_kdesc_lo(sm + B::X0_HI), w_x0l = lp_tc_kdesc_lo(sm + B::X0_LO);
-  unsigned long long *bar = bars + 2 * grp, *bar_dw = bars + 2 * grp + 1;
-  int phase = 0, n_dw = 0;
-  const int num_tiles = (R.n + GT - 1) / GT;
-  const int tot = M.S + M.S_inf;
-
-  // A round trip to the tensor core is split in two so that independent work can run while the MMAs
-  // execute: HANDOFF publishes this thread's staged operand row and lets the leader issue (ISSUE ends
-  // with the commit to `bar`); WAIT blocks until the result is in tensor memory.
-#if LP_TC_ISSUERS == 4
-#define LP_ISSUE(A, WH, WL, KS, K0, NS, N, FIRST, LO, WI) lp_issue_layer_part(tbase, BT_D, A, WH, WL, KS, K0, NS, N, LO, WI)
-#define LP_ISSUE_DW() lp_issue_dw_part<C>(tmem, gs, wi)
-#define LP_ISSUE_ENCW() lp_issue_encw_part<C>(tmem, gs, wi)
-#else
-#define LP_ISSUE(A, WH, WL, KS, K0, NS, N, FIRST, LO, WI) lp_issue_layer(tbase, BT_D, A, WH, WL, KS, K0, NS, N, FIRST, LO)
-#define LP_ISSUE_DW() lp_issue_dw<C>(tmem, gs, 1)
-#define LP_ISSUE_ENCW() lp_issue_encw<C>(tmem, gs, 1)
-#endif
-#ifdef LP_ABL_NO_SYNC  // profiling only (results are garbage): no hand-off, no MMAs, no waits
-#define LP_TC_HANDOFF(ISSUE)
-#define LP_TC_WAIT()
-#else
-#define LP_TC_HANDOFF(ISSUE) LP_TCG_HANDOFF(1 + grp, GTH, leader, ISSUE)
-#define LP_TC_WAIT() LP_TCG_WAIT(bar, phase)
-#endif
-#define LP_TC_ROUND(ISSUE) LP_TC_HANDOFF(ISSUE) LP_TC_WAIT()
-
-  for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
-    const Ray1 me = lp_load_ray1(R, tile * GT + s, G.g[0].B);
-    const int q = me.active ? me.ray : R.n - 1;
-    {
-      float e[W];
-      const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)q * H + fc);
-#pragma unroll
-      for (int k = 0; k < W / 4; ++k) {
-        const float4 v = __ldg(e4 + k);
-        e[4 * k] = v.x; e[4 * k + 1] = v.y; e[4 * k + 2] = v.z; e[4 * k + 3] = v.w;
-      }
-      lp_stage_row<W, 16>(tme + BT_E + pk, e);
-    }
-    LpCompBwd cb;  // per-ray constants and running state of the compositing gradient
-    cb.init(io, q, me.active, D.n_feat);
-    float S[W];  // sum over steps of the colour-hidden gradient (this part's columns)
-#pragma unroll
-    for (int j = 0; j < W; ++j) S[j] = 0.f;
-
-    // Software pipeline across steps: the gather of step n+1 is issued while the tensor core runs the
-    // first input-gradient product of step n, and the scatter of step n while it runs the first layer
-    // of step n+1 -- the two memory-bound, MMA-independent pieces hide inside the waits.
-    struct Pos { float depth, delta, x, y, z, oob, occ; };
-    auto sample_at = [&](int step) {
-      Pos p;
-      const Sched sc = lp_sched(step, M);
-      lp_depth_delta(sc, me.near, me.far, p.depth, p.delta);
-      p.x = me.ox + p.depth * me.dx; p.y = me.oy + p.depth * me.dy; p.z = me.oz + p.depth * me.dz;
-      if (M.contract) lp_contract(p.x, p.y, p.z);
-      p.oob = M.mask_oob ? lp_in_bounds(p.x, p.y, p.z) : 1.f;
-      p.occ = SCAF ? lp_nearest(SC, me.b, p.x, p.y, p.z) : 1.f;
-      return p;
-    };
-    Pos cur = sample_at(0), prev = cur;
-    float x0[CW], dxp[CW];  // gathered features of the current step; input gradient of the previous step
-    bool cur_hit = lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
-    bool have_prev = false;
-    // Empty-space folding (see the forward kernel).  With all-zero features every activation of the step is a
-    // per-ray constant and the whole backward sweep is LINEAR in the four compositing gradients (g_raw, dlogit_0..2),
-    // so steps at which all 128 samples of the group are empty only accumulate those four scalars (G, L0..2) and
-    // one extra iteration per ray tile ("virt", step = tot) runs the sweep once with the sums.  Iteration
-    // step = -1 ("probe") evaluates the decoder at zero features for the compositing of the empty steps.
-    float e_raw = 0.f, e_lg0 = 0.f, e_lg1 = 0.f, e_lg2 = 0.f, G_raw = 0.f, L0 = 0.f, L1 = 0.f, L2 = 0.f;
-    bool any_empty = false;
-
-    auto composite = [&](float raw, float lg0, float lg1, float lg2, int step, float& g_raw, float& dl0, float& dl1, float& dl2) {
-      cb.grad(M, me.ray, step, step == tot - 1, raw, lg0, lg1, lg2, cur.depth, cur.delta, SCAF ? cur.occ : 1.f, g_raw, dl0, dl1, dl2);
-    };
-
-    for (int step = LP_TC_EMPTY_FOLD ? -1 : 0; step < tot + (LP_TC_EMPTY_FOLD ? 1 : 0); ++step) {
-      const bool probe = step < 0, virt = step == tot, real = !probe && !virt;
-      if (virt && !any_empty) break;
-      float v[W];
-      // occupancy scaffold (renderer_bw.py, as renderer_fw.py:234-252): a step whose 128 samples are all in empty
-      // space has zero weight and zero gradient and is skipped by the whole group (the pipeline just advances)
-      if (SCAF && real && !lp_bar_any(1 + grp, GTH, cur.occ != 0.f)) {
-        if (step + 1 < tot) {
-          cur = sample_at(step + 1);
-          cur_hit = lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
-        }
-        continue;
-      }
-      // the previous step's parameter-gradient products must have consumed the tiles
-#ifndef LP_ABL_NO_SYNC
-      if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
-#endif
-      if (real) {
-        lp_tile_row<CW>(gs + B::A1, 8 + (CW / 8) * h, s, x0);
-        lp_stage_row<CW, 32>(tme + BT_A + (CW / 2) * h, x0);
-      } else {
-        float z0[CW];
-#pragma unroll
-        for (int c = 0; c < CW; ++c) z0[c] = 0.f;
-        lp_tile_row<CW>(gs + B::A1, 8 + (CW / 8) * h, s, z0);
-        lp_stage_row<CW, 32>(tme + BT_A + (CW / 2) * h, z0);
-      }
-      // ------------------------------ forward recompute ------------------------------
-#if LP_TC_EMPTY_FOLD && !defined(LP_ABL_NO_SYNC)
-      lp_tmem_wait_st();
-      lp_tc_fence_before();
-      if (!(lp_bar_any(1 + grp, GTH, real && cur_hit) || !real)) {  // every sample of the group is empty
-        float g_raw, dl0, dl1, dl2;
-        composite(e_raw, e_lg0, e_lg1, e_lg2, step, g_raw, dl0, dl1, dl2);
-        G_raw += g_raw; L0 += dl0; L1 += dl1; L2 += dl2;
-        any_empty = true;
-        if (step + 1 < tot) {
-          cur = sample_at(step + 1);
-          cur_hit = lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
-        }
-        continue;
-      }
-      if (leader) {
-        lp_tc_fence_after();
-        LP_ISSUE(BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, true, 32, wi);
-        lp_tc_commit(bar);
-      }
-#else
-      LP_TC_HANDOFF(LP_ISSUE(BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, true, 32, wi); lp_tc_commit(bar));
-#endif
-      if (have_prev) {
-        if (me.active && prev.oob != 0.f) lp_splat_regs<C, CW>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp, CW * h);
-        have_prev = false;
-      }
-      LP_TC_WAIT();
-      lp_tmem_ld<W>(tme + BT_D + fc, v);
-      LP_TC_ZERO(W, tme + BT_D + fc);
-#pragma unroll
-      for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j] + F[I::FB + fc + j], 0.f);
-      lp_tile_row<W>(gs + B::A1, 0 + ck, s, v);
-      lp_stage_row<W, 32>(tme + BT_A + pk, v);
-      LP_TC_ROUND(LP_ISSUE(BT_A, w_t1h, w_t1l, 2, 0, 512, 32, true, 32, wi); lp_tc_commit(bar));
-      lp_tmem_ld<W>(tme + BT_D + fc, v);
-      LP_TC_ZERO(W, tme + BT_D + fc);
-#pragma unroll
-      for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j] + F[I::FB + 32 + fc + j], 0.f);
-      lp_tile_row<W>(gs + B::A1, 4 + ck, s, v);
-      lp_stage_row<W, 32>(tme + BT_A + pk, v);
-      LP_TC_ROUND(LP_ISSUE(BT_A, w_och, w_ocl, 2, 0, 1024, 64, true, 32, wi);
-                  LP_ISSUE(BT_E, w_och, w_ocl, 2, 2, 1024, 64, false, 16, wi - 2); lp_tc_commit(bar));
-      float raw = 0.f, lg0 = 0.f, lg1 = 0.f, lg2 = 0.f;  // this part's share of the output layer
-      lp_tmem_ld<W>(tme + BT_D + fc, v);
-      LP_TC_ZERO(W, tme + BT_D + fc);
-#pragma unroll
-      for (int j = 0; j < W; ++j) {
-        v[j] = fmaxf(v[j] + F[I::FB + 64 + fc + j], 0.f);
-        raw = fmaf(v[j], F[I::FWO + fc + j], raw);
-      }
-      lp_tile_row<W>(gs + B::A2, 0 + ck, s, v);
-      lp_tmem_ld<W>(tme + BT_D + 32 + fc, v);
-      LP_TC_ZERO(W, tme + BT_D + 32 + fc);
-#pragma unroll
-      for (int j = 0; j < W; ++j) {
-        v[j] = fmaxf(v[j] + F[I::FB + 96 + fc + j], 0.f);
-        const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * (fc + j));
-        lg0 = fmaf(v[j], w.x, lg0); lg1 = fmaf(v[j], w.y, lg1); lg2 = fmaf(v[j], w.z, lg2);
-      }
-      lp_tile_row<W>(gs + B::A2, 4 + ck, s, v);
-      if (NP == 2) {  // combine the two parts' partial sums (both then run the same compositing arithmetic)
-        xch[h * GT + s] = make_float4(lg0, lg1, lg2, raw);
-#ifndef LP_ABL_NO_SYNC
-        lp_bar_sync(1 + grp, GTH);
-#endif
-        const float4 o = xch[(h ^ 1) * GT + s];
-        lg0 += o.x; lg1 += o.y; lg2 += o.z; raw += o.w;
-      }
-      raw += F[I::FBL + 3]; lg0 += F[I::FBL]; lg1 += F[I::FBL + 1]; lg2 += F[I::FBL + 2];
-      if (probe) {  // decoder output at zero features, for the compositing of the empty steps
-        e_raw = raw; e_lg0 = lg0; e_lg1 = lg1; e_lg2 = lg2;
-        continue;
-      }
-      // ------------------------------ compositing gradient ------------------------------
-      float g_raw, dl0, dl1, dl2;
-      if (!virt) composite(raw, lg0, lg1, lg2, step, g_raw, dl0, dl1, dl2);
-      else { g_raw = G_raw; dl0 = L0; dl1 = L1; dl2 = L2; }  // the summed gradients of the tile's empty steps
-      if (h == 0) lp_tile8(gs + B::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
-      // ------------------------------ backward sweep ------------------------------
-#pragma unroll
-      for (int j = 0; j < W; ++j) v[j] = g_raw * F[I::FWO + fc + j];  // d_ho
-      lp_gate_row<W>(v, gs + B::A2, 0 + ck, s);
-      lp_tile_row<W>(gs + B::DY, 4 + ck, s, v);
-      lp_stage_row<W, 32>(tme + BT_A + pk, v);
-#pragma unroll
-      for (int j = 0; j < W; ++j) {                                     // d_hc
-        const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * (fc + j));
-        v[j] = fmaf(dl0, w.x, fmaf(dl1, w.y, dl2 * w.z));
-      }
-      lp_gate_row<W>(v, gs + B::A2, 4 + ck, s);
-#pragma unroll
-      for (int j = 0; j < W; ++j) S[j] += v[j];
-      lp_tile_row<W>(gs + B::DY, 8 + ck, s, v);
-      lp_stage_row<W, 32>(tme + BT_A + 16 + pk, v);
-      LP_TC_HANDOFF(LP_ISSUE(BT_A, w_xth, w_xtl, 4, 0, 1024, 32, true, 32, wi); lp_tc_commit(bar));
-      if (!virt) prev = cur;
-      if (step + 1 < tot) {  // prefetch the next step's features while the product runs
-        cur = sample_at(step + 1);
-        cur_hit = lp_gather_regs<C, CW>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0, CW * h);
-      }
-      LP_TC_WAIT();
-      lp_tmem_ld<W>(tme + BT_D + fc, v);
-      LP_TC_ZERO(W, tme + BT_D + fc);
-      lp_gate_row<W>(v, gs + B::A1, 4 + ck, s);  // d_t
-      lp_tile_row<W>(gs + B::DY, 0 + ck, s, v);
-      lp_stage_row<W, 32>(tme + BT_A + pk, v);
-      LP_TC_ROUND(LP_ISSUE(BT_A, w_xhh, w_xhl, 2, 0, 512, 32, true, 32, wi); lp_tc_commit(bar));
-      lp_tmem_ld<W>(tme + BT_D + fc, v);
-      LP_TC_ZERO(W, tme + BT_D + fc);
-      lp_gate_row<W>(v, gs + B::A1, 0 + ck, s);  // d_h1
-      lp_tile_row<W>(gs + B::DY, 12 + ck, s, v);
-      lp_stage_row<W, 32>(tme + BT_A + pk, v);
-      lp_fence_async_smem();  // this step's tile writes -> visible to the tensor core
-      LP_TC_ROUND(LP_ISSUE(BT_A, w_x0h, w_x0l, 2, 0, 512, C, true, 32, wi); lp_tc_commit(bar);
-                  LP_ABL_DW(LP_ISSUE_DW()); lp_tc_commit(bar_dw));
-      ++n_dw;
-      lp_tmem_ld<CW>(tme + BT_D + CW * h, dxp);
-      LP_TC_ZERO(CW, tme + BT_D + CW * h);
-#pragma unroll
-      for (int c = 0; c < CW; ++c) dxp[c] *= prev.oob;
-      have_prev = !virt;  // (zero features touch no texel: the fold iteration has nothing to scatter)
-    }
-    if (have_prev && me.active && prev.oob != 0.f)  // last step's scatter
-      lp_splat_regs<C, CW>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp, CW * h);
-    // ---- per-tile tail: encoding gradient = S Wc0^T, and the encoding's share of dWc0 = enc^T S ----
-#ifndef LP_ABL_NO_SYNC
-    if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
-#endif
-    {
-      float e[W];
-      const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)q * H + fc);
-#pragma unroll
-      for (int k = 0; k < W / 4; ++k) {
-        const float4 vv = __ldg(e4 + k);
-        e[4 * k] = vv.x; e[4 * k + 1] = vv.y; e[4 * k + 2] = vv.z; e[4 * k + 3] = vv.w;
-      }
-      lp_tile_row<W>(gs + B::A1, 0 + ck, s, e);
-      lp_tile_row<W>(gs + B::DY, 8 + ck, s, S);
-      lp_stage_row<W, 32>(tme + BT_A + 16 + pk, S);  // K index 32..63 of the d_t weight tile = colour hidden
-      lp_fence_async_smem();
-      float v[W];
-      LP_TC_ROUND(LP_ISSUE(BT_A + 16, w_xth, w_xtl, 2, 2, 1024, 32, true, 32, wi); lp_tc_commit(bar);
-                  LP_ISSUE_ENCW(); lp_tc_commit(bar_dw));
-      ++n_dw;
-      lp_tmem_ld<W>(tme + BT_D + fc, v);
-      LP_TC_ZERO(W, tme + BT_D + fc);
-      if (me.active) {
-        float4* ge = reinterpret_cast<float4*>(io.g_enc + (long long)me.ray * H + fc);
-#pragma unroll
-        for (int k = 0; k < W / 4; ++k) ge[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-      }
-    }
-  }
-#undef LP_TC_ROUND
-#undef LP_TC_HANDOFF
-#undef LP_TC_WAIT
-#undef LP_ISSUE
-#undef LP_ISSUE_DW
-#undef LP_ISSUE_ENCW
-#undef LP_TC_ZERO
-  // ---- drain, then the CTA's first four warps read the accumulators (TMEM lane = stack row) ----
-#ifndef LP_ABL_NO_SYNC
-  if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
-#endif
-  lp_tc_fence_before();
-  __syncthreads();
-  lp_tc_fence_after();
-  if (warp < 4) {
-    const LpLayer &t0 = D.trunk.l[0], &t1 = D.trunk.l[1], &o0 = D.opacity.l[0], &o1 = D.opacity.l[1],
-                  &c0 = D.color.l[0], &c1 = D.color.l[1];
-    float v[32];
-    const unsigned tl = lp_taddr(tmem, warp, 0);
-    auto add_rows = [&](const LpLayer& Ly, int col) {  // this lane's stack row of a 32-column product
-      lp_tmem_ld32u(tl + col, v);
-#pragma unroll
-      for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Ly.w_off + lane * Ly.N + n, v[n]);
-    };
-    if (warp == 0) {         // stack rows 0..31: h1 (x d_t), and the encoding product
-      add_rows(t1, BT_W + 0);
-      add_rows(c0, BT_ENC);
-    } else if (warp == 1) {  // rows 32..63: trunk output (x d_ho, x d_hc)
-      add_rows(o0, BT_W + 32);
-      add_rows(c0, BT_W + 64);
-    } else if (warp == 2) {  // rows 64..64+C: grid features (x d_h1)
-      lp_tmem_ld32u(tl + BT_W + 96, v);
-      if (lane < C)
-        for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + t0.w_off + lane * t0.N + n, v[n]);
-    }
-    constexpr int ones_warp = (64 + C) / 32, ones_lane = (64 + C) % 32;  // the row of ones: bias gradients
-    if (warp == ones_warp) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        lp_tmem_ld32u(tl + BT_W + 32 * j, v);
-        const LpLayer& Lb = j == 0 ? t1 : (j == 1 ? o0 : (j == 2 ? c0 : t0));
-        if (lane == ones_lane)
-          for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Lb.b_off + n, v[n]);
-      }
-    }
-    // last layer (A2 x DYL): rows 0..31 opacity hidden, 32..63 colour hidden, 64 ones; columns dlogit_0..2, g_raw
-    if (warp < 3) {
-      lp_tmem_ld32u(tl + BT_L, v);  // 16 valid columns (the rest belongs to the next accumulator)
-      if (warp == 0) {
-        lp_red_add1(io.g_params + o1.w_off + lane * o1.N, v[3]);
-      } else if (warp == 1) {
-        for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.w_off + lane * c1.N + c, v[c]);
-      } else if (lane == 0) {
-        for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.b_off + c, v[c]);
-        lp_red_add1(io.g_params + o1.b_off, v[3]);
-      }
-    }
-  }
-  lp_tc_fence_before();
-  __syncthreads();
-  if (tid < 32) lp_tmem_dealloc512(tmem);
-}
-
-#ifndef LP_TC_BWD_NP
-#define LP_TC_BWD_NP 1  // threads per sample in the backward kernel (2 halves the registers per thread; measured equal or slower)
-#endif
-template <int C, bool SCAF>
-static int lp_tc_render_backward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
-  const int groups = 2;
-  constexpr int NP = LP_TC_BWD_NP;
-  const size_t bytes = BImg<C>::GROUPS + (size_t)groups * BImg<C>::GROUP_BYTES;
-  if (LP_TC_SET_SMEM((lp_render_bwd_tc_kernel<C, NP, SCAF>), bytes)) return LP_ERR_CUDA;
-  const int tiles = (a.R.n + GT - 1) / GT;
-  int blocks = (tiles + groups - 1) / groups;
-  const int max_blocks = lp_tc_num_sms();
-  if (blocks > max_blocks) blocks = max_blocks;
-  LP_LAUNCH((lp_render_bwd_tc_kernel<C, NP, SCAF>), dim3(blocks), dim3(groups * GT * NP), bytes, st, a.R, a.M, a.D, a.G, a.SC, params, io);
-  return LP_OK;
-}
-static inline int lp_tc_render_backward(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
-  if (a.use_scaffold)
-    return a.D.C == 16 ? lp_tc_render_backward_t<16, true>(st, a, params, io) : lp_tc_render_backward_t<32, true>(st, a, params, io);
-  return a.D.C == 16 ? lp_tc_render_backward_t<16, false>(st, a, params, io) : lp_tc_render_backward_t<32, false>(st, a, params, io);
-}
 
 }  // namespace lptc

@@ -82,6 +82,7 @@ def lightplane_renderer(
     regenerate_code: bool = False,
     triton_block_size: int = 16,
     triton_num_warps: int = 4,
+    ray_image_width: Optional[int] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Render `rays` through the feature grid-list `grid` (emission-absorption ray march).
 
@@ -89,6 +90,11 @@ def lightplane_renderer(
     beyond far, equispaced in disparity) the grid-list is tri/bi-linearly sampled, decoded by
     trunk -> (opacity, colour) MLPs and alpha-composited.  Arguments and semantics are those
     of the reference (lightplane_renderer.py:54-211).
+
+    `ray_image_width` (extension, optional): when the N rays are a row-major image of that width
+    (a multiple of 16, with a multiple of 8 rows) the kernels walk them in 16x8-pixel tiles, which
+    makes the gathers / gradient reductions of a warp texel-coherent.  A scheduling hint only:
+    results are those of the default order up to floating-point summation order.
 
     Returns `(ray_length_render [N], negative_log_transmittance [N], feature_render [N, color_chn])`.
     """
@@ -130,6 +136,7 @@ def lightplane_renderer(
         float(disparity_at_inf),
         float(inject_noise_sigma),
         int(inject_noise_seed),
+        int(ray_image_width or 0),
     )
 
 
@@ -166,6 +173,7 @@ class LightplaneFunction(torch.autograd.Function):
         disparity_at_inf: float,
         inject_noise_sigma: float,
         inject_noise_seed: int,
+        ray_image_width: int = 0,
     ):
         lib = _cabi.get_lib()
         device = feature_grid.device
@@ -245,6 +253,7 @@ class LightplaneFunction(torch.autograd.Function):
             inject_noise_sigma,
             inject_noise_seed,
             num_rays,
+            ray_image_width,
         )
         spec = _cabi.DecoderSpec(
             n_t, n_o, n_c, hid_t, hid_o, hid_c, dim_in_trunk, dim_in_opacity, dim_in_color,
@@ -322,7 +331,7 @@ class LightplaneFunction(torch.autograd.Function):
         else:
             grad_enc.zero_()
 
-        return (grad_grid, grad_mlp, grad_enc, grad_color) + (None,) * 17
+        return (grad_grid, grad_mlp, grad_enc, grad_color) + (None,) * 18
 
 
 def _byref(s):

@@ -180,6 +180,7 @@ class LightplaneRenderer(torch.nn.Module):
         rays_jitter_near_far: Optional[bool] = None,
         return_log_transmittance: Optional[bool] = None,
         regenerate_code: Optional[bool] = None,
+        ray_image_width: Optional[int] = None,
     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Render; every keyword overrides the module default for this call
         (renderer_module.py:419-563).  Returns `(ray_length, alpha, features)` where alpha is
@@ -225,6 +226,7 @@ class LightplaneRenderer(torch.nn.Module):
             color_grid=color_feature_grid,
             grid_sizes=grid_sizes,
             color_grid_sizes=color_grid_sizes,
+            ray_image_width=ray_image_width,
         )
         transmittance = torch.exp(-nlt)
         features = features + transmittance[..., None] * bg

@@ -22,7 +22,7 @@ def decoder_spec(c):
     )
 
 
-def render_case(lib, c, device):
+def render_case(lib, c, device, ray_image_width=0):
     """forward + backward of a renderer golden case through the raw C-ABI."""
     f = lambda k: c[k].to(device=device, dtype=torch.float32).contiguous()
     cfgd = renderer_cfg(c)
@@ -37,7 +37,7 @@ def render_case(lib, c, device):
     cfg = _cabi.make_cfg(cfgd["num_samples"], cfgd["num_samples_inf"], cfgd["gain"],
                          cfgd["disparity_at_inf"], cfgd["mask_out_of_bounds_samples"],
                          cfgd["contract_coords"], cfgd["inject_noise_sigma"],
-                         cfgd["inject_noise_seed"], n)
+                         cfgd["inject_noise_seed"], n, ray_image_width)
     spec = decoder_spec(c)
     rays = _cabi.make_rays(dirs, orig, gidx, near, far, enc)
     gl = _cabi.make_grid_list(grid, sizes)

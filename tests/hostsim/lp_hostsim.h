@@ -221,6 +221,15 @@ static inline void lp_mbar_wait(unsigned long long* bar, int parity) {
   while ((int)(std::atomic_ref<unsigned long long>(*bar).load(std::memory_order_acquire) & 1ull) == parity)
     std::this_thread::yield();
 }
+static inline void lp_hs_mbar_arrive(unsigned long long* bar) {
+  std::atomic_ref<unsigned long long> a(*bar);
+  unsigned long long o = a.load(std::memory_order_acquire), n;
+  do {
+    const unsigned long long expect = o >> 48, arrived = ((o >> 32) & 0xffffull) + 1;
+    n = arrived == expect ? ((o & 0xffff0000ffffffffull) + 1) : (o + (1ull << 32));
+  } while (!a.compare_exchange_weak(o, n, std::memory_order_acq_rel));
+}
+static inline void lp_mbar_arrive(unsigned long long* bar) { lp_hs_mbar_arrive(bar); }
 static inline void lp_fence_async_smem() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void lp_tc_fence_before() {}
 static inline void lp_tc_fence_after() {}

@@ -127,3 +127,13 @@ def test_hostsim_layer_counts_empty_space_folding(lib):
     for k, v in got.items():
         tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
         assert rel_err(v, want[k]) < tol, (k, rel_err(v, want[k]))
+
+
+def test_hostsim_renderer_tile_walk_hint(lib):
+    """`ray_image_width`: the same rays walked as 16x8-pixel tiles give the same results up to summation order (the
+    MMAs of a product accumulate in issue order, gradient reductions in arrival order)."""
+    c = coherent_case(load_case("render_triplane_inf_gain"), n=256, pixel=0.02, mask_oob=0)
+    a = render_case(lib, c, "cpu")
+    b = render_case(lib, c, "cpu", ray_image_width=16)
+    for k in a:
+        assert rel_err(a[k], b[k]) < (2e-5 if k != "g_mlp" else 2e-3), (k, rel_err(a[k], b[k]))
