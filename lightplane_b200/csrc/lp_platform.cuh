@@ -299,6 +299,9 @@ LP_DEVICE void lp_tmem_ld(unsigned taddr, float (&v)[N]) {
     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
   }
 }
+// register re-allocation between warp-specialised roles (all warps of a 128-thread warpgroup execute it)
+#define LP_SETMAXNREG_INC(n) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(n))
+#define LP_SETMAXNREG_DEC(n) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(n))
 // named barrier over `nthreads` threads (ids 1..15; 0 is __syncthreads)
 LP_DEVICE void lp_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // named barrier with an OR reduction: true iff `pred` holds for any of the `nthreads` threads

@@ -218,8 +218,16 @@ static inline float lp_hs_trunc_tf32(float x) {
 static inline void lp_mbar_init(unsigned long long* bar, int count) { *bar = (unsigned long long)count << 48; }
 static inline void lp_mbar_init_fence() {}
 static inline void lp_mbar_wait(unsigned long long* bar, int parity) {
-  while ((int)(std::atomic_ref<unsigned long long>(*bar).load(std::memory_order_acquire) & 1ull) == parity)
+  unsigned long spins = 0;
+  while ((int)(std::atomic_ref<unsigned long long>(*bar).load(std::memory_order_acquire) & 1ull) == parity) {
     std::this_thread::yield();
+    if (++spins == (1ul << 22) && getenv("LP_HOSTSIM_WATCHDOG")) {  // debugging aid: report a stuck wait once
+      const unsigned long long v = std::atomic_ref<unsigned long long>(*bar).load();
+      fprintf(stderr, "[hostsim] thread %u block %u stuck on mbarrier at smem+%ld parity %d (phases %llu arrived %llu expect %llu)\n",
+              lp_hostsim::g_ctx->tid.x, lp_hostsim::g_ctx->bid.x, (long)((unsigned char*)bar - lp_hostsim::g_ctx->block->smem), parity,
+              v & 0xffffffffull, (v >> 32) & 0xffffull, v >> 48);
+    }
+  }
 }
 static inline void lp_hs_mbar_arrive(unsigned long long* bar) {
   std::atomic_ref<unsigned long long> a(*bar);
@@ -230,6 +238,8 @@ static inline void lp_hs_mbar_arrive(unsigned long long* bar) {
   } while (!a.compare_exchange_weak(o, n, std::memory_order_acq_rel));
 }
 static inline void lp_mbar_arrive(unsigned long long* bar) { lp_hs_mbar_arrive(bar); }
+#define LP_SETMAXNREG_INC(n)
+#define LP_SETMAXNREG_DEC(n)
 static inline void lp_fence_async_smem() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void lp_tc_fence_before() {}
 static inline void lp_tc_fence_after() {}
@@ -359,6 +369,7 @@ static inline void lp_bar_sync(int id, int nthreads) {
     if (!b->named[id]) b->named[id].reset(new std::barrier<>(nthreads));
     bar = b->named[id].get();
   }
+  if (getenv("LP_HOSTSIM_TRACE")) fprintf(stderr, "[hostsim] t%u bar.sync id %d n %d\n", lp_hostsim::g_ctx->tid.x, id, nthreads);
   bar->arrive_and_wait();
 }
 static inline bool lp_bar_any(int id, int nthreads, bool pred) {

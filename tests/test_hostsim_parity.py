@@ -136,4 +136,4 @@ def test_hostsim_renderer_tile_walk_hint(lib):
     a = render_case(lib, c, "cpu")
     b = render_case(lib, c, "cpu", ray_image_width=16)
     for k in a:
-        assert rel_err(a[k], b[k]) < (2e-5 if k != "g_mlp" else 2e-3), (k, rel_err(a[k], b[k]))
+        assert rel_err(a[k], b[k]) < (1e-4 if k != "g_mlp" else 2e-3), (k, rel_err(a[k], b[k]))
