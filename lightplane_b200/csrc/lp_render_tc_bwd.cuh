@@ -2,10 +2,12 @@
 // thread-per-sample tcgen05 kernel, see lp_render_tc.cuh for the scheme and DESIGN.md section 4.
 //
 // Per step and group of 128 rays: forward recompute (three round trips to the tensor core, bf16 hi+lo three-product
-// form = fp32-grade), compositing gradient per thread, then the input-gradient chain d_t -> d_h1 -> d_x0 as ONE
-// kind::tf32 product per layer: the gradient rows are stored to tensor memory as rounded fp32 words (no hi/lo split),
-// the transposed weights sit in shared memory as tf32 K-major tiles.  SURVEY.md H3: only the forward / recompute needs
-// fp32-grade products; single-pass TF32 input-gradient products keep grid / encoding gradients at ~5e-4.
+// form = fp32-grade), compositing gradient per thread, then the input-gradient chain d_t -> d_h1 -> d_x0.  SURVEY.md H3:
+// only the forward / recompute needs fp32-grade products.  The widest input-gradient product, [d_ho | d_hc] (K = 64) ->
+// d_t, is ONE kind::tf32 product: the gradient row goes to tensor memory as rounded fp32 words (no hi/lo split, a
+// third of the MMAs), its transposed weights are a tf32 K-major tile.  With all three products in TF32 the grid
+// gradient measured 0.8-1.0e-3 off the reference's Triton kernels on the same B200 (profiles/gpu_comparator_r2.md) --
+// at north_star's 1e-3 bar -- so d_t -> d_h1 -> d_x0 keep the three-product bf16 form.
 // The parameter gradients dW = X^T dY are MN-major bf16 tile products accumulated in tensor memory for the whole kernel.
 //
 // Reference semantics: lightplane/triton_src/templates/renderer_bw.py:89-627.
@@ -15,52 +17,12 @@
 
 namespace lptc {
 
-// Shared memory after the forward image: the transposed weights of the three input-gradient products as tf32 K-major
-// tiles (element (n, k) at (n/8)*nstride + (k/4)*128 + (n%8)*16 + (k%4)*4), then per group the bf16 operand tiles of
-// the parameter-gradient GEMMs
-//     dW = A^T dY  over the group's 128 samples (the MMA's K),
-// all MN-major: element (row, sample s) at (row/8)*2048 + (s/8)*128 + (s%8)*16 + (row%8)*2, so a thread
-// writes 8 features of its sample as one 16-byte store.
-//   A1 = [h1 | trunk out | x0 | ones]   (rows 0-31, 32-63, 64..64+C, 64+C)       x  DY = [d_t | d_ho | d_hc | d_h1] (N = 128)
-//   A2 = [opacity hidden | colour hidden | ones]                                  x  DYL = [dlogit_0..2, g_raw, 0...] (N = 16)
-template <int C>
-struct BImg {
-  using I = Img<C>;
-  static constexpr int XT = (I::FWD_END + 127) / 128 * 128;  // d_t:  [32 trunk][64: opacity hidden | colour hidden], nstride 2048
-  static constexpr int XH = XT + 8192;                       // d_h1: [32][32], nstride 1024
-  static constexpr int X0 = XH + 4096;                       // d_x0: [C][32], nstride 1024
-  static constexpr int BARS = X0 + C * 128;                  // mbarriers + TMEM slot (128 B)
-  static constexpr int GROUPS = BARS + 128;
-  // per-group tiles
-  static constexpr int ONES1 = 8 + C / 8;                    // chunk of A1 whose first row is all ones
-  static constexpr int A1 = 0;
-  static constexpr int A2 = A1 + (ONES1 + 1) * 2048;
-  static constexpr int DY = A2 + 9 * 2048;
-  static constexpr int DYL = DY + 16 * 2048;
-  static constexpr int GROUP_BYTES = DYL + 2 * 2048;
-  static_assert(A2 + 16 * 2048 <= GROUP_BYTES, "operand window leaves the group's region");
-};
-// tensor-memory columns: per group A 0..63 (recompute: packed bf16 hi 0..15 / lo 32..47; input gradients: fp32 tf32
-// words, [d_ho | d_hc] 0..63), encoding (hi 64..79, lo 80..95), D 96..159; shared by the CTA: the dW accumulators
-constexpr int BT_A = 0, BT_E = 64, BT_D = 96, BT_GROUP_COLS = 160;
+// tensor-memory columns shared by the CTA: the parameter-gradient accumulators (A1 x DY, A2 x DYL, encoding x S)
 constexpr int BT_W = 320, BT_L = 448, BT_ENC = 464;
 
 LP_DEVICE void lp_put_w_tf32(unsigned char* sm, int off, int n, int k, int K, float w) {
   *reinterpret_cast<unsigned*>(sm + off + (n >> 3) * (K >> 2) * 128 + (k >> 2) * 128 + (n & 7) * 16 + (k & 3) * 4) = lp_tf32_rna(w);
 }
-template <int C>
-LP_DEVICE void lp_build_bimg(unsigned char* sm, const float* __restrict__ P, const LpDecoder& D) {
-  using B = BImg<C>;
-  const LpLayer &t0 = D.trunk.l[0], &t1 = D.trunk.l[1], &o0 = D.opacity.l[0], &c0 = D.color.l[0];
-  const int tid = threadIdx.x, nth = blockDim.x;
-  for (int e = tid; e < 32 * 64; e += nth) {  // B[n = trunk feature][k]: k < 32 opacity hidden k, else colour hidden k-32
-    const int n = e >> 6, k = e & 63;
-    lp_put_w_tf32(sm, B::XT, n, k, 64, k < 32 ? P[o0.w_off + n * o0.N + k] : P[c0.w_off + n * c0.N + (k - 32)]);
-  }
-  for (int e = tid; e < 32 * 32; e += nth) lp_put_w_tf32(sm, B::XH, e >> 5, e & 31, 32, P[t1.w_off + (e >> 5) * t1.N + (e & 31)]);
-  for (int e = tid; e < C * 32; e += nth) lp_put_w_tf32(sm, B::X0, e >> 5, e & 31, 32, P[t0.w_off + (e >> 5) * t0.N + (e & 31)]);
-}
-
 // store a row of N gradients as this thread's row of a kind::tf32 A operand (one fp32 word per column)
 template <int N>
 LP_DEVICE void lp_stage_row_tf32(unsigned taddr, const float (&x)[N]) {
@@ -78,422 +40,14 @@ LP_DEVICE void lp_issue_tf32_part(unsigned tbase, int d_col, int a_col, lp_kdesc
   }
 }
 
-// the group's parameter-gradient products over its 128 samples (8 k-steps of 16)
-template <int C>
-LP_DEVICE void lp_issue_dw(unsigned tmem, unsigned char* gs, int accumulate) {
-  using B = BImg<C>;
-  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), a2 = lp_tc_mndesc_lo(gs + B::A2), dy = lp_tc_mndesc_lo(gs + B::DY),
-                   dyl = lp_tc_mndesc_lo(gs + B::DYL);
-#pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
-    lp_tc_mma_ss_mn(tmem + BT_W, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 128, accumulate | (ks > 0));
-    lp_tc_mma_ss_mn(tmem + BT_L, lp_tc_kadv(a2, ks * 256), lp_tc_kadv(dyl, ks * 256), 2048, 16, accumulate | (ks > 0));
-  }
-}
-// issuer wi of 4: k-steps 2wi, 2wi+1 of both products
-template <int C>
-LP_DEVICE void lp_issue_dw_part(unsigned tmem, unsigned char* gs, int wi) {
-  using B = BImg<C>;
-  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), a2 = lp_tc_mndesc_lo(gs + B::A2), dy = lp_tc_mndesc_lo(gs + B::DY),
-                   dyl = lp_tc_mndesc_lo(gs + B::DYL);
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int ks = 2 * wi + j;
-    lp_tc_mma_ss_mn(tmem + BT_W, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 128, 1);
-    lp_tc_mma_ss_mn(tmem + BT_L, lp_tc_kadv(a2, ks * 256), lp_tc_kadv(dyl, ks * 256), 2048, 16, 1);
-  }
-}
-// encoding^T x (step-sum of the colour-hidden gradient): A1 chunks 0-3 hold the encodings, DY chunks 8-11 the sums
-template <int C>
-LP_DEVICE void lp_issue_encw_part(unsigned tmem, unsigned char* gs, int wi) {
-  using B = BImg<C>;
-  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), dy = lp_tc_mndesc_lo(gs + B::DY + 8 * 2048);
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int ks = 2 * wi + j;
-    lp_tc_mma_ss_mn(tmem + BT_ENC, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 32, 1);
-  }
-}
-template <int C>
-LP_DEVICE void lp_issue_encw(unsigned tmem, unsigned char* gs, int accumulate) {
-  using B = BImg<C>;
-  const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + B::A1), dy = lp_tc_mndesc_lo(gs + B::DY + 8 * 2048);
-#pragma unroll
-  for (int ks = 0; ks < 8; ++ks)
-    lp_tc_mma_ss_mn(tmem + BT_ENC, lp_tc_kadv(a1, ks * 256), lp_tc_kadv(dy, ks * 256), 2048, 32, accumulate | (ks > 0));
-}
-
 #ifdef LP_ABL_NO_DW
 #define LP_ABL_DW(x)
 #else
 #define LP_ABL_DW(x) x
 #endif
 
-template <int C, bool SCAF>
-__global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G, LpGridSet SC,
-                                                                   const float* __restrict__ params, LpBwdIo io) {
-  using I = Img<C>;
-  using B = BImg<C>;
-  LP_DYN_SMEM(unsigned char, sm);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = tid / GT, ngroups = blockDim.x / GT, s = tid % GT, wig = (tid >> 5) & 3;  // sample row, TMEM lane quarter
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + B::BARS);  // [2g] round trips, [2g+1] dW; [8] init
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 10);
-  unsigned char* gs = sm + B::GROUPS + grp * B::GROUP_BYTES;
-  lp_build_img<C>(sm, params, D);
-  lp_build_bimg<C>(sm, params, D);
-  for (int e = s; e < B::GROUP_BYTES / 16; e += GT) reinterpret_cast<uint4*>(gs)[e] = make_uint4(0u, 0u, 0u, 0u);
-  __syncthreads();
-  {  // rows of ones (bf16 1.0): first row of A1 chunk ONES1 and of A2 chunk 8
-    *reinterpret_cast<unsigned short*>(gs + B::A1 + B::ONES1 * 2048 + (s >> 3) * 128 + (s & 7) * 16) = 0x3F80;
-    *reinterpret_cast<unsigned short*>(gs + B::A2 + 8 * 2048 + (s >> 3) * 128 + (s & 7) * 16) = 0x3F80;
-  }
-  if (tid == 0) {
-    for (int i = 0; i < 8; ++i) lp_mbar_init(bars + i, 4);  // four issuing threads per group
-    lp_mbar_init(bars + 8, 1);
-    lp_mbar_init_fence();
-  }
-  if (tid < 32) lp_tmem_alloc512(tmem_slot);
-  lp_fence_async_smem();
-  lp_tc_fence_before();
-  __syncthreads();
-  lp_tc_fence_after();
-  const unsigned tmem = *tmem_slot;
-  if (tid == 0) {  // zero the accumulators: products of the (all-zero) gradient tiles with accumulate off
-    lp_issue_dw<C>(tmem, gs, 0);
-    lp_issue_encw<C>(tmem, gs, 0);
-    lp_tc_commit(bars + 8);
-  }
-  lp_mbar_wait(bars + 8, 0);
-  lp_tc_fence_after();
-  __syncthreads();
-
-  const unsigned tbase = tmem + (unsigned)(grp * BT_GROUP_COLS);
-  const unsigned tme = lp_taddr(tbase, wig, 0);
-  const bool leader = lane == 0;  // lane 0 of each of the group's four warps issues its share of every product
-  const int wi = wig;
-  const float* F = reinterpret_cast<const float*>(sm + I::F32);
-  lp_tmem_zero<32>(tme + BT_D);
-  lp_tmem_zero<32>(tme + BT_D + 32);
-  const lp_kdesc_t w_t0h = lp_tc_kdesc_lo(sm + I::T0_HI), w_t0l = lp_tc_kdesc_lo(sm + I::T0_LO),
-                   w_t1h = lp_tc_kdesc_lo(sm + I::T1_HI), w_t1l = lp_tc_kdesc_lo(sm + I::T1_LO),
-                   w_och = lp_tc_kdesc_lo(sm + I::OC_HI), w_ocl = lp_tc_kdesc_lo(sm + I::OC_LO),
-                   w_xt = lp_tc_kdesc_lo(sm + B::XT), w_xh = lp_tc_kdesc_lo(sm + B::XH), w_x0 = lp_tc_kdesc_lo(sm + B::X0);
-  unsigned long long *bar = bars + 2 * grp, *bar_dw = bars + 2 * grp + 1;
-  int phase = 0, n_dw = 0;
-  const int num_tiles = (R.n + GT - 1) / GT;
-  const int tot = M.S + M.S_inf;
-
-  // A round trip to the tensor core is split in two so that independent work can run while the MMAs
-  // execute: HANDOFF publishes this thread's staged operand row and lets the leaders issue (ISSUE ends
-  // with the commit to `bar`); WAIT blocks until the result is in tensor memory.
-#define LP_ISSUE(A, WH, WL, KS, K0, NS, N, LO, WI) lp_issue_layer_part(tbase, BT_D, A, WH, WL, KS, K0, NS, N, LO, WI)
-#define LP_ISSUE_TF32(A, W, KS, K0, NS, N) lp_issue_tf32_part(tbase, BT_D, A, W, KS, K0, NS, N, wi)
-#ifdef LP_ABL_NO_SYNC  // profiling only (results are garbage): no hand-off, no MMAs, no waits
-#define LP_TC_HANDOFF(ISSUE)
-#define LP_TC_WAIT()
-#else
-#define LP_TC_HANDOFF(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, leader, ISSUE)
-#define LP_TC_WAIT() LP_TCG_WAIT(bar, phase)
-#endif
-#define LP_TC_ROUND(ISSUE) LP_TC_HANDOFF(ISSUE) LP_TC_WAIT()
-
-  for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
-    const Ray1 me = lp_load_ray1(R, lp_tile_ray(M, tile, s), G.g[0].B);
-    const int q = me.active ? me.ray : R.n - 1;
-    {
-      float e[32];
-      const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)q * H);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 v = __ldg(e4 + k);
-        e[4 * k] = v.x; e[4 * k + 1] = v.y; e[4 * k + 2] = v.z; e[4 * k + 3] = v.w;
-      }
-      lp_stage_row<32, 16>(tme + BT_E, e);
-    }
-    LpCompBwd cb;  // per-ray constants and running state of the compositing gradient
-    cb.init(io, q, me.active, D.n_feat);
-    float S[32];  // sum over steps of the colour-hidden gradient
-#pragma unroll
-    for (int j = 0; j < 32; ++j) S[j] = 0.f;
-
-    // Software pipeline across steps: the gather of step n+1 is issued while the tensor core runs the
-    // first input-gradient product of step n, and the scatter of step n while it runs the first layer
-    // of step n+1 -- the two memory-bound, MMA-independent pieces hide inside the waits.
-    struct Pos { float depth, delta, x, y, z, oob, occ; };
-    auto sample_at = [&](int step) {
-      Pos p;
-      const Sched sc = lp_sched(step, M);
-      lp_depth_delta(sc, me.near, me.far, p.depth, p.delta);
-      p.x = me.ox + p.depth * me.dx; p.y = me.oy + p.depth * me.dy; p.z = me.oz + p.depth * me.dz;
-      if (M.contract) lp_contract(p.x, p.y, p.z);
-      p.oob = M.mask_oob ? lp_in_bounds(p.x, p.y, p.z) : 1.f;
-      p.occ = SCAF ? lp_nearest(SC, me.b, p.x, p.y, p.z) : 1.f;
-      return p;
-    };
-    Pos cur = sample_at(0), prev = cur;
-    float x0[C], dxp[C];  // gathered features of the current step; input gradient of the previous step
-    bool cur_hit = lp_gather_regs<C>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
-    bool have_prev = false;
-    // Empty-space folding (see the forward kernel).  With all-zero features every activation of the step is a
-    // per-ray constant and the whole backward sweep is LINEAR in the four compositing gradients (g_raw, dlogit_0..2),
-    // so steps at which all 128 samples of the group are empty only accumulate those four scalars (G, L0..2) and
-    // one extra iteration per ray tile ("virt", step = tot) runs the sweep once with the sums.  Iteration
-    // step = -1 ("probe") evaluates the decoder at zero features for the compositing of the empty steps.
-    float e_raw = 0.f, e_lg0 = 0.f, e_lg1 = 0.f, e_lg2 = 0.f, G_raw = 0.f, L0 = 0.f, L1 = 0.f, L2 = 0.f;
-    bool any_empty = false;
-
-    auto composite = [&](float raw, float lg0, float lg1, float lg2, int step, float& g_raw, float& dl0, float& dl1, float& dl2) {
-      cb.grad(M, me.ray, step, step == tot - 1, raw, lg0, lg1, lg2, cur.depth, cur.delta, SCAF ? cur.occ : 1.f, g_raw, dl0, dl1, dl2);
-    };
-
-    for (int step = LP_TC_EMPTY_FOLD ? -1 : 0; step < tot + (LP_TC_EMPTY_FOLD ? 1 : 0); ++step) {
-      const bool probe = step < 0, virt = step == tot, real = !probe && !virt;
-      if (virt && !any_empty) break;
-      float v[32];
-      // occupancy scaffold (renderer_bw.py, as renderer_fw.py:234-252): a step whose 128 samples are all in empty
-      // space has zero weight and zero gradient and is skipped by the whole group (the pipeline just advances)
-      if (SCAF && real && !lp_bar_any(1 + grp, GT, cur.occ != 0.f)) {
-        if (step + 1 < tot) {
-          cur = sample_at(step + 1);
-          cur_hit = lp_gather_regs<C>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
-        }
-        continue;
-      }
-      // the previous step's parameter-gradient products must have consumed the tiles
-#ifndef LP_ABL_NO_SYNC
-      if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
-#endif
-      if (real) {
-        lp_tile_row<C>(gs + B::A1, 8, s, x0);
-        lp_stage_row<C, 32>(tme + BT_A, x0);
-      } else {
-        float z0[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) z0[c] = 0.f;
-        lp_tile_row<C>(gs + B::A1, 8, s, z0);
-        lp_stage_row<C, 32>(tme + BT_A, z0);
-      }
-      // ------------------------------ forward recompute ------------------------------
-#if LP_TC_EMPTY_FOLD && !defined(LP_ABL_NO_SYNC)
-      lp_tmem_wait_st();
-      lp_tc_fence_before();
-      if (!(lp_bar_any(1 + grp, GT, real && cur_hit) || !real)) {  // every sample of the group is empty
-        float g_raw, dl0, dl1, dl2;
-        composite(e_raw, e_lg0, e_lg1, e_lg2, step, g_raw, dl0, dl1, dl2);
-        G_raw += g_raw; L0 += dl0; L1 += dl1; L2 += dl2;
-        any_empty = true;
-        if (step + 1 < tot) {
-          cur = sample_at(step + 1);
-          cur_hit = lp_gather_regs<C>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
-        }
-        continue;
-      }
-      if (leader) {
-        lp_tc_fence_after();
-        LP_ISSUE(BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, 32, wi);
-        lp_tc_commit(bar);
-      }
-#else
-      LP_TC_HANDOFF(LP_ISSUE(BT_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, 32, wi); lp_tc_commit(bar));
-#endif
-      if (have_prev) {
-        if (me.active && prev.oob != 0.f) lp_splat_regs<C>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp);
-        have_prev = false;
-      }
-      LP_TC_WAIT();
-      lp_tmem_ld<32>(tme + BT_D, v);
-      lp_tmem_zero<32>(tme + BT_D);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + j], 0.f);
-      lp_tile_row<32>(gs + B::A1, 0, s, v);
-      lp_stage_row<32, 32>(tme + BT_A, v);
-      LP_TC_ROUND(LP_ISSUE(BT_A, w_t1h, w_t1l, 2, 0, 512, 32, 32, wi); lp_tc_commit(bar));
-      lp_tmem_ld<32>(tme + BT_D, v);
-      lp_tmem_zero<32>(tme + BT_D);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + 32 + j], 0.f);
-      lp_tile_row<32>(gs + B::A1, 4, s, v);
-      lp_stage_row<32, 32>(tme + BT_A, v);
-      LP_TC_ROUND(LP_ISSUE(BT_A, w_och, w_ocl, 2, 0, 1024, 64, 32, wi);
-                  LP_ISSUE(BT_E, w_och, w_ocl, 2, 2, 1024, 64, 16, wi - 2); lp_tc_commit(bar));
-      float raw, lg0, lg1, lg2;
-      {  // output layer (4 wide) on the CUDA cores, exact fp32; two partial sums per output shorten the FMA chains
-        float r0 = F[I::FBL + 3], r1 = 0.f;
-        lp_tmem_ld<32>(tme + BT_D, v);
-        lp_tmem_zero<32>(tme + BT_D);
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          v[j] = fmaxf(v[j] + F[I::FB + 64 + j], 0.f);
-          v[j + 1] = fmaxf(v[j + 1] + F[I::FB + 64 + j + 1], 0.f);
-          r0 = fmaf(v[j], F[I::FWO + j], r0);
-          r1 = fmaf(v[j + 1], F[I::FWO + j + 1], r1);
-        }
-        raw = r0 + r1;
-        lp_tile_row<32>(gs + B::A2, 0, s, v);
-        float a0 = F[I::FBL], a1 = F[I::FBL + 1], a2 = F[I::FBL + 2], b0 = 0.f, b1 = 0.f, b2 = 0.f;
-        lp_tmem_ld<32>(tme + BT_D + 32, v);
-        lp_tmem_zero<32>(tme + BT_D + 32);
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          v[j] = fmaxf(v[j] + F[I::FB + 96 + j], 0.f);
-          v[j + 1] = fmaxf(v[j + 1] + F[I::FB + 96 + j + 1], 0.f);
-          const float4 w0 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
-          const float4 w1 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j + 4);
-          a0 = fmaf(v[j], w0.x, a0); a1 = fmaf(v[j], w0.y, a1); a2 = fmaf(v[j], w0.z, a2);
-          b0 = fmaf(v[j + 1], w1.x, b0); b1 = fmaf(v[j + 1], w1.y, b1); b2 = fmaf(v[j + 1], w1.z, b2);
-        }
-        lg0 = a0 + b0; lg1 = a1 + b1; lg2 = a2 + b2;
-        lp_tile_row<32>(gs + B::A2, 4, s, v);
-      }
-      if (probe) {  // decoder output at zero features, for the compositing of the empty steps
-        e_raw = raw; e_lg0 = lg0; e_lg1 = lg1; e_lg2 = lg2;
-        continue;
-      }
-      // ------------------------------ compositing gradient ------------------------------
-      float g_raw, dl0, dl1, dl2;
-      if (!virt) composite(raw, lg0, lg1, lg2, step, g_raw, dl0, dl1, dl2);
-      else { g_raw = G_raw; dl0 = L0; dl1 = L1; dl2 = L2; }  // the summed gradients of the tile's empty steps
-      lp_tile8(gs + B::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
-      // ------------------------------ backward sweep (kind::tf32, one product per layer) ------------------------------
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = g_raw * F[I::FWO + j];  // d_ho
-      lp_gate_row<32>(v, gs + B::A2, 0, s);
-      lp_tile_row<32>(gs + B::DY, 4, s, v);
-      lp_stage_row_tf32<32>(tme + BT_A, v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {                                     // d_hc
-        const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
-        v[j] = fmaf(dl0, w.x, fmaf(dl1, w.y, dl2 * w.z));
-      }
-      lp_gate_row<32>(v, gs + B::A2, 4, s);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) S[j] += v[j];
-      lp_tile_row<32>(gs + B::DY, 8, s, v);
-      lp_stage_row_tf32<32>(tme + BT_A + 32, v);
-      LP_TC_HANDOFF(LP_ISSUE_TF32(BT_A, w_xt, 8, 0, 2048, 32); lp_tc_commit(bar));
-      if (!virt) prev = cur;
-      if (step + 1 < tot) {  // prefetch the next step's features while the product runs
-        cur = sample_at(step + 1);
-        cur_hit = lp_gather_regs<C>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
-      }
-      LP_TC_WAIT();
-      lp_tmem_ld<32>(tme + BT_D, v);
-      lp_tmem_zero<32>(tme + BT_D);
-      lp_gate_row<32>(v, gs + B::A1, 4, s);  // d_t
-      lp_tile_row<32>(gs + B::DY, 0, s, v);
-      lp_stage_row_tf32<32>(tme + BT_A, v);
-      LP_TC_ROUND(LP_ISSUE_TF32(BT_A, w_xh, 4, 0, 1024, 32); lp_tc_commit(bar));
-      lp_tmem_ld<32>(tme + BT_D, v);
-      lp_tmem_zero<32>(tme + BT_D);
-      lp_gate_row<32>(v, gs + B::A1, 0, s);  // d_h1
-      lp_tile_row<32>(gs + B::DY, 12, s, v);
-      lp_stage_row_tf32<32>(tme + BT_A, v);
-      lp_fence_async_smem();  // this step's tile writes -> visible to the tensor core
-      LP_TC_ROUND(LP_ISSUE_TF32(BT_A, w_x0, 4, 0, 1024, C); lp_tc_commit(bar);
-                  LP_ABL_DW(lp_issue_dw_part<C>(tmem, gs, wi)); lp_tc_commit(bar_dw));
-      ++n_dw;
-      lp_tmem_ld<C>(tme + BT_D, dxp);
-      lp_tmem_zero<C>(tme + BT_D);
-#pragma unroll
-      for (int c = 0; c < C; ++c) dxp[c] *= prev.oob;
-      have_prev = !virt;  // (zero features touch no texel: the fold iteration has nothing to scatter)
-    }
-    if (have_prev && me.active && prev.oob != 0.f)  // last step's scatter
-      lp_splat_regs<C>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp);
-    // ---- per-tile tail: encoding gradient = S Wc0^T, and the encoding's share of dWc0 = enc^T S ----
-#ifndef LP_ABL_NO_SYNC
-    if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
-#endif
-    {
-      float e[32];
-      const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)q * H);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 vv = __ldg(e4 + k);
-        e[4 * k] = vv.x; e[4 * k + 1] = vv.y; e[4 * k + 2] = vv.z; e[4 * k + 3] = vv.w;
-      }
-      lp_tile_row<32>(gs + B::A1, 0, s, e);
-      lp_tile_row<32>(gs + B::DY, 8, s, S);
-      lp_stage_row_tf32<32>(tme + BT_A + 32, S);  // K index 32..63 of the d_t weight tile = colour hidden
-      lp_fence_async_smem();
-      float v[32];
-      LP_TC_ROUND(LP_ISSUE_TF32(BT_A + 32, w_xt, 4, 4, 2048, 32); lp_tc_commit(bar);
-                  lp_issue_encw_part<C>(tmem, gs, wi); lp_tc_commit(bar_dw));
-      ++n_dw;
-      lp_tmem_ld<32>(tme + BT_D, v);
-      lp_tmem_zero<32>(tme + BT_D);
-      if (me.active) {
-        float4* ge = reinterpret_cast<float4*>(io.g_enc + (long long)me.ray * H);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ge[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-      }
-    }
-  }
-#undef LP_TC_ROUND
-#undef LP_TC_HANDOFF
-#undef LP_TC_WAIT
-#undef LP_ISSUE
-#undef LP_ISSUE_TF32
-  // ---- drain, then the CTA's first four warps read the accumulators (TMEM lane = stack row) ----
-#ifndef LP_ABL_NO_SYNC
-  if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
-#endif
-  lp_tc_fence_before();
-  __syncthreads();
-  lp_tc_fence_after();
-  if (warp < 4) {
-    const LpLayer &t0 = D.trunk.l[0], &t1 = D.trunk.l[1], &o0 = D.opacity.l[0], &o1 = D.opacity.l[1],
-                  &c0 = D.color.l[0], &c1 = D.color.l[1];
-    float v[32];
-    const unsigned tl = lp_taddr(tmem, warp, 0);
-    auto add_rows = [&](const LpLayer& Ly, int col) {  // this lane's stack row of a 32-column product
-      lp_tmem_ld32u(tl + col, v);
-#pragma unroll
-      for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Ly.w_off + lane * Ly.N + n, v[n]);
-    };
-    if (warp == 0) {         // stack rows 0..31: h1 (x d_t), and the encoding product
-      add_rows(t1, BT_W + 0);
-      add_rows(c0, BT_ENC);
-    } else if (warp == 1) {  // rows 32..63: trunk output (x d_ho, x d_hc)
-      add_rows(o0, BT_W + 32);
-      add_rows(c0, BT_W + 64);
-    } else if (warp == 2) {  // rows 64..64+C: grid features (x d_h1)
-      lp_tmem_ld32u(tl + BT_W + 96, v);
-      if (lane < C)
-        for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + t0.w_off + lane * t0.N + n, v[n]);
-    }
-    constexpr int ones_warp = (64 + C) / 32, ones_lane = (64 + C) % 32;  // the row of ones: bias gradients
-    if (warp == ones_warp) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        lp_tmem_ld32u(tl + BT_W + 32 * j, v);
-        const LpLayer& Lb = j == 0 ? t1 : (j == 1 ? o0 : (j == 2 ? c0 : t0));
-        if (lane == ones_lane)
-          for (int n = 0; n < 32; ++n) lp_red_add1(io.g_params + Lb.b_off + n, v[n]);
-      }
-    }
-    // last layer (A2 x DYL): rows 0..31 opacity hidden, 32..63 colour hidden, 64 ones; columns dlogit_0..2, g_raw
-    if (warp < 3) {
-      lp_tmem_ld32u(tl + BT_L, v);  // 16 valid columns (the rest belongs to the next accumulator)
-      if (warp == 0) {
-        lp_red_add1(io.g_params + o1.w_off + lane * o1.N, v[3]);
-      } else if (warp == 1) {
-        for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.w_off + lane * c1.N + c, v[c]);
-      } else if (lane == 0) {
-        for (int c = 0; c < D.n_feat; ++c) lp_red_add1(io.g_params + c1.b_off + c, v[c]);
-        lp_red_add1(io.g_params + o1.b_off, v[3]);
-      }
-    }
-  }
-  lp_tc_fence_before();
-  __syncthreads();
-  if (tid < 32) lp_tmem_dealloc512(tmem);
-}
-
-
 // =====================================================================================================================
-// Warp-specialised backward (default).  Same arithmetic as lp_render_bwd_tc_kernel above; what changes is WHO does it:
+// Warp-specialised backward: WHO does what
 //
 //   threads   0..255  two decoder groups (128 threads = 128 rays each): recompute, compositing gradient, input-gradient
 //                     chain, parameter-gradient tiles -- everything that talks to the tensor core;
@@ -521,12 +75,16 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tc_kernel(LpRays R, LpMa
 template <int C>
 struct SImg {
   using I = Img<C>;
-  static constexpr int XT = (I::FWD_END + 127) / 128 * 128;  // tf32 tiles of the input-gradient products (as BImg)
-  static constexpr int XH = XT + 8192;
-  static constexpr int X0 = XH + 4096;
-  static constexpr int BARS = X0 + C * 128;                  // 16 mbarriers + TMEM slot + flags (256 B)
-  static constexpr int OCC = BARS + 256;                     // [2 groups][2][128] floats: occupancy of the slot's samples (scaffold)
-  static constexpr int GROUPS = OCC + 2048;
+  // transposed weights of the input-gradient products:
+  static constexpr int XT = (I::FWD_END + 127) / 128 * 128;  // d_t:  tf32 [32 trunk][64: opacity hidden | colour hidden], K-major:
+                                                             //       (n, k) at (n/8)*2048 + (k/4)*128 + (n%8)*16 + (k%4)*4
+  static constexpr int XH_HI = XT + 8192;                    // d_h1: bf16 hi / lo [32][32], K-major as the forward tiles
+  static constexpr int XH_LO = XH_HI + 2048;
+  static constexpr int X0_HI = XH_LO + 2048;                 // d_x0: bf16 hi / lo [C][32]
+  static constexpr int X0_LO = X0_HI + C * 64;
+  static constexpr int BARS = X0_LO + C * 64;                // 17 mbarriers + TMEM slot + flags (256 B)
+  static constexpr int OCC = BARS + 256;                     // [2 groups][128] floats: occupancy of the slot's samples (scaffold)
+  static constexpr int GROUPS = OCC + 1024;
   // per-group dW operand tiles, one stack shared by both products:
   //   chunks: ho 0-3 | hc 4-7 | ones 8 | x0 9.. | h1 | trunk      A2 = chunks 0.. (ho, hc, ones), A1 = chunks 8.. (ones, x0, h1, trunk)
   static constexpr int CH_HO = 0, CH_HC = 4, CH_ONES = 8, CH_X0 = 9, CH_H1 = 9 + C / 8, CH_TR = CH_H1 + 4, CH_END = CH_TR + 4;
@@ -540,6 +98,18 @@ struct SImg {
 };
 constexpr int ST_A = 0, ST_X = 64, ST_D = 96, ST_GROUP_COLS = 160;  // X: hi 64.., lo 80..; d_x0 lands in D columns 32..
 
+template <int C>
+LP_DEVICE void lp_build_simg(unsigned char* sm, const float* __restrict__ P, const LpDecoder& D) {
+  using W = SImg<C>;
+  const LpLayer &t0 = D.trunk.l[0], &t1 = D.trunk.l[1], &o0 = D.opacity.l[0], &c0 = D.color.l[0];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int e = tid; e < 32 * 64; e += nth) {  // B[n = trunk feature][k]: k < 32 opacity hidden k, else colour hidden k-32
+    const int n = e >> 6, k = e & 63;
+    lp_put_w_tf32(sm, W::XT, n, k, 64, k < 32 ? P[o0.w_off + n * o0.N + k] : P[c0.w_off + n * c0.N + (k - 32)]);
+  }
+  for (int e = tid; e < 32 * 32; e += nth) lp_put_w(sm, W::XH_HI, W::XH_LO, e >> 5, e & 31, 32, P[t1.w_off + (e >> 5) * t1.N + (e & 31)]);
+  for (int e = tid; e < C * 32; e += nth) lp_put_w(sm, W::X0_HI, W::X0_LO, e >> 5, e & 31, 32, P[t0.w_off + (e >> 5) * t0.N + (e & 31)]);
+}
 template <int C>
 LP_DEVICE void lp_ws_issue_dw_part(unsigned tmem, unsigned char* gs, int wi) {
   using W = SImg<C>;
@@ -582,11 +152,10 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + W::BARS);
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 18);
   int* flags = reinterpret_cast<int*>(bars + 20) + 2 * grp;  // [2]: 0 every sample of the slot is empty, 1 full slot, 2 unoccupied (scaffold)
-  float* occs = reinterpret_cast<float*>(sm + W::OCC) + grp * 256;
+  float* occs = reinterpret_cast<float*>(sm + W::OCC) + grp * GT;
   unsigned char* gs = sm + W::GROUPS + grp * W::GROUP_BYTES;
   lp_build_img<C>(sm, params, D);
-  lp_build_bimg<C>(sm, params, D);  // XT / XH / X0 sit at the same offsets in BImg and SImg
-  static_assert(W::XT == BImg<C>::XT && W::X0 == BImg<C>::X0, "tf32 tiles");
+  lp_build_simg<C>(sm, params, D);
   for (int e = tid; e < 2 * W::GROUP_BYTES / 16; e += blockDim.x) reinterpret_cast<uint4*>(sm + W::GROUPS)[e] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   if (is_mlp)  // the row of ones (bf16 1.0): first row of chunk CH_ONES
@@ -627,7 +196,6 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
   const int num_tiles = (R.n + GT - 1) / GT;
   const int tot = M.S + M.S_inf;
   const int tile0 = blockIdx.x * 2 + grp, tile_stride = gridDim.x * 2;
-  const int s_off = (s >> 3) * 128 + (s & 7) * 16;  // this sample's 16-byte slot inside a tile chunk
 
   if (!is_mlp) {
     // =================================================================================================================
@@ -666,7 +234,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           lp_tmem_wait_st();
           lp_tc_fence_before();
         }
-        if (SCAF) occs[(n_slot & 1) * GT + s] = occ;
+        if (SCAF) occs[s] = occ;  // (single buffer: the decoder thread reads it before it releases x0_free)
         if (s == 0) flags[n_slot & 1] = flag;
         lp_mbar_arrive(x0_full);
         ++n_slot;
@@ -733,9 +301,11 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
     const lp_kdesc_t w_t0h = lp_tc_kdesc_lo(sm + I::T0_HI), w_t0l = lp_tc_kdesc_lo(sm + I::T0_LO),
                      w_t1h = lp_tc_kdesc_lo(sm + I::T1_HI), w_t1l = lp_tc_kdesc_lo(sm + I::T1_LO),
                      w_och = lp_tc_kdesc_lo(sm + I::OC_HI), w_ocl = lp_tc_kdesc_lo(sm + I::OC_LO),
-                     w_xt = lp_tc_kdesc_lo(sm + W::XT), w_xh = lp_tc_kdesc_lo(sm + W::XH), w_x0 = lp_tc_kdesc_lo(sm + W::X0);
+                     w_xt = lp_tc_kdesc_lo(sm + W::XT), w_xhh = lp_tc_kdesc_lo(sm + W::XH_HI), w_xhl = lp_tc_kdesc_lo(sm + W::XH_LO),
+                     w_x0h = lp_tc_kdesc_lo(sm + W::X0_HI), w_x0l = lp_tc_kdesc_lo(sm + W::X0_LO);
     int phase = 0, phase0 = 0, n_dw = 0, n_slot = 0, n_dx = 0, n_xt = 0;
 #define LP_ISSUE(A, WH, WL, KS, K0, NS, N, LO, WI) lp_issue_layer_part(tbase, ST_D, A, WH, WL, KS, K0, NS, N, LO, WI)
+#define LP_ISSUE_D(DC, A, WH, WL, KS, K0, NS, N, LO, WI) lp_issue_layer_part(tbase, DC, A, WH, WL, KS, K0, NS, N, LO, WI)
 #define LP_ISSUE_TF32(DC, A, W_, KS, K0, NS, N) lp_issue_tf32_part(tbase, DC, A, W_, KS, K0, NS, N, wi)
 #define LP_TC_HANDOFF(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, leader, ISSUE)
 #define LP_TC_WAIT() LP_TCG_WAIT(bar, phase)
@@ -778,7 +348,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         // ---- the slot's operand, flag and occupancy from the memory group ----
         lp_mbar_wait(x0_full, n_slot & 1);
         const int flag = flags[n_slot & 1];
-        const float occ = SCAF ? occs[(n_slot & 1) * GT + s] : 1.f;
+        const float occ = SCAF ? occs[s] : 1.f;
         ++n_slot;
         float depth = 0.f, delta = 0.f;
         if (!probe && !virt) {
@@ -867,7 +437,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         if (!virt) cb.grad(M, ray, step, step == tot - 1, raw, lg0, lg1, lg2, depth, delta, occ, g_raw, dl0, dl1, dl2);
         else { g_raw = G_raw; dl0 = L0; dl1 = L1; dl2 = L2; }  // the summed gradients of the tile's empty steps
         lp_tile8(gs + W::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
-        // ------------------------------ backward sweep (kind::tf32, one product per layer) ------------------------------
+        // ------------------------------ backward sweep ------------------------------
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = g_raw * F[I::FWO + j];  // d_ho
         lp_gate_row<32>(v, gs + W::STK, W::CH_HO, s);
@@ -888,16 +458,16 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         lp_tmem_zero<32>(tme + ST_D);
         lp_gate_row<32>(v, gs + W::STK, W::CH_TR, s);  // d_t
         lp_tile_row<32>(gs + W::DY, 0, s, v);
-        lp_stage_row_tf32<32>(tme + ST_A, v);
-        LP_TC_ROUND(LP_ISSUE_TF32(ST_D, ST_A, w_xh, 4, 0, 1024, 32); lp_tc_commit(bar));
+        lp_stage_row<32, 32>(tme + ST_A, v);
+        LP_TC_ROUND(LP_ISSUE(ST_A, w_xhh, w_xhl, 2, 0, 512, 32, 32, wi); lp_tc_commit(bar));
         lp_tmem_ld<32>(tme + ST_D, v);
         lp_tmem_zero<32>(tme + ST_D);
         lp_gate_row<32>(v, gs + W::STK, W::CH_H1, s);  // d_h1
         lp_tile_row<32>(gs + W::DY, 12, s, v);
-        lp_stage_row_tf32<32>(tme + ST_A, v);
+        lp_stage_row<32, 32>(tme + ST_A, v);
         lp_fence_async_smem();  // this step's tile writes -> visible to the tensor core
         // last product of the slot: d_x0 (for the memory group) and the dW GEMM; nobody here waits for them
-        LP_TC_HANDOFF(LP_ISSUE_TF32(ST_D + 32, ST_A, w_x0, 4, 0, 1024, C); lp_tc_commit(dx_full);
+        LP_TC_HANDOFF(LP_ISSUE_D(ST_D + 32, ST_A, w_x0h, w_x0l, 2, 0, 512, C, 32, wi); lp_tc_commit(dx_full);
                       lp_mbar_wait(xt_full, n_xt & 1); LP_ABL_DW(lp_ws_issue_dw_part<C>(tmem, gs, wi)); lp_tc_commit(bar_dw));
         ++n_dw; ++n_dx; ++n_xt;
       }
@@ -932,6 +502,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
 #undef LP_TC_WAIT
 #undef LP_ISSUE
 #undef LP_ISSUE_TF32
+#undef LP_ISSUE_D
   }
   // ---- drain, then the CTA's first four warps read the accumulators (TMEM lane = stack row) ----
   lp_tc_fence_before();
@@ -977,9 +548,6 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
   if (tid < 32) lp_tmem_dealloc512(tmem);
 }
 
-#ifndef LP_TC_BWD_WS
-#define LP_TC_BWD_WS 1  // 1: warp-specialised backward (lp_render_bwd_ws_kernel), 0: lp_render_bwd_tc_kernel
-#endif
 template <int C, bool SCAF>
 static int lp_tc_render_backward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {
   const int groups = 2;
@@ -987,15 +555,9 @@ static int lp_tc_render_backward_t(cudaStream_t st, const LpRenderArgs& a, const
   int blocks = (tiles + groups - 1) / groups;
   const int max_blocks = lp_tc_num_sms();
   if (blocks > max_blocks) blocks = max_blocks;
-#if LP_TC_BWD_WS
   const size_t bytes = SImg<C>::GROUPS + (size_t)groups * SImg<C>::GROUP_BYTES;
   if (LP_TC_SET_SMEM((lp_render_bwd_ws_kernel<C, SCAF>), bytes)) return LP_ERR_CUDA;
   LP_LAUNCH((lp_render_bwd_ws_kernel<C, SCAF>), dim3(blocks), dim3(2 * groups * GT), bytes, st, a.R, a.M, a.D, a.G, a.SC, params, io);
-#else
-  const size_t bytes = BImg<C>::GROUPS + (size_t)groups * BImg<C>::GROUP_BYTES;
-  if (LP_TC_SET_SMEM((lp_render_bwd_tc_kernel<C, SCAF>), bytes)) return LP_ERR_CUDA;
-  LP_LAUNCH((lp_render_bwd_tc_kernel<C, SCAF>), dim3(blocks), dim3(groups * GT), bytes, st, a.R, a.M, a.D, a.G, a.SC, params, io);
-#endif
   return LP_OK;
 }
 static inline int lp_tc_render_backward(cudaStream_t st, const LpRenderArgs& a, const float* params, const LpBwdIo& io) {

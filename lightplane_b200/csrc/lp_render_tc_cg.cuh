@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(384, 1) lp_render_bwd_cg_kernel(LpRays R, LpMa
         lg0 = fmaf(v[j], w.x, lg0); lg1 = fmaf(v[j], w.y, lg1); lg2 = fmaf(v[j], w.z, lg2);
       }
       lp_tile_row<32>(gs + I::A2, 4, s, v);
-      // ------------------------------ compositing gradient (as lp_render_bwd_tc_kernel) ------------------------------
+      // ------------------------------ compositing gradient (as lp_render_bwd_ws_kernel) ------------------------------
       float g_raw, dl0, dl1, dl2;
       cb.grad(M, me.ray, step, step == tot - 1, raw, lg0, lg1, lg2, depth, delta, 1.f, g_raw, dl0, dl1, dl2);
       lp_tile8(gs + I::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);

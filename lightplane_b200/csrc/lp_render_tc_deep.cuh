@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(128, 1) lp_render_bwd_deep_kernel(LpRays R, Lp
 #pragma unroll
     for (int j = 0; j < 32; ++j) S[j] = 0.f;
 
-    // empty-space folding (see lp_render_bwd_tc_kernel): probe iteration, summed gradients of the empty steps, one fold iteration
+    // empty-space folding (see lp_render_bwd_ws_kernel): probe iteration, summed gradients of the empty steps, one fold iteration
     float e_raw = 0.f, e_lg0 = 0.f, e_lg1 = 0.f, e_lg2 = 0.f, G_raw = 0.f, L0 = 0.f, L1 = 0.f, L2 = 0.f;
     bool any_empty = false;
     for (int step = LP_TC_EMPTY_FOLD ? -1 : 0; step < tot + (LP_TC_EMPTY_FOLD ? 1 : 0); ++step) {
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(128, 1) lp_render_bwd_deep_kernel(LpRays R, Lp
         lp_tile_row<32>(tl, I::LIN + 4, s, e);
       }
       raw += F[I::FBL + 3]; lg0 += F[I::FBL]; lg1 += F[I::FBL + 1]; lg2 += F[I::FBL + 2];
-      // ------------------------------ compositing gradient (as lp_render_bwd_tc_kernel) ------------------------------
+      // ------------------------------ compositing gradient (as lp_render_bwd_ws_kernel) ------------------------------
       if (probe) { e_raw = raw; e_lg0 = lg0; e_lg1 = lg1; e_lg2 = lg2; continue; }
       float g_raw, dl0, dl1, dl2;
       if (!virt) cb.grad(M, me.ray, step, step == tot - 1, raw, lg0, lg1, lg2, depth, delta, occ, g_raw, dl0, dl1, dl2);

@@ -236,7 +236,7 @@ static inline int lp_tcw_render_forward(cudaStream_t st, const LpRenderArgs& a, 
 // ===========================================================================================
 // One group of 256 threads per SM: two threads per sample (thread part h owns columns [32h, 32h+32) of every 64-wide
 // row and half of the grid channels), so that the per-thread code and register budget are those of the width-32
-// kernel.  What differs from lp_render_bwd_tc_kernel, all forced by one SM's shared memory (227 KB) and tensor
+// kernel.  What differs from lp_render_bwd_ws_kernel, all forced by one SM's shared memory (227 KB) and tensor
 // memory (512 columns):
 //  * no transposed weight copies: the input-gradient products read the FORWARD weight tiles as MN-major operands
 //    (lp_tc_mma_ts_t); opacity and colour hidden layers are separate products (D is 64 columns);
