@@ -169,6 +169,16 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle (a port of the reference's naive PyTorch path) on the host cores
 # ---------------------------------------------------------------------------------------------
+def host_threads():
+    """Threads for the CPU arm: the cores this process may run on, at most 64 (beyond that the chunked PyTorch oracle
+    only thrashes: 128 threads measured 50x slower than 64 on the GPU box)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
 def oracle_problem(n_rays, seed=0):
     """A small instance of the bench workload on CPU tensors (same camera model, grid, decoder init)."""
     import lightplane_b200 as lp
@@ -234,7 +244,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     torch.set_num_threads(threads)  # torchrun exports OMP_NUM_THREADS=1: pin the arm to the box's cores explicitly
     n_rays, chunk = 8192, 2048
     for _ in range(args.warmup):
@@ -464,7 +474,7 @@ def main():
         }
         cpu = None
         if world == 1 and not args.skip_cpu_baseline and not cfg5:
-            torch.set_num_threads(os.cpu_count() or 1)
+            torch.set_num_threads(host_threads())
             oracle_fwd_bwd(oracle_problem(4096), 2048)  # warm-up
             prob = oracle_problem(16384, seed=1)
             dt, ofeat, ogrid, omlp = oracle_fwd_bwd(prob, 2048)

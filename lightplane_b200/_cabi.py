@@ -160,7 +160,10 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
     """Contiguous fp32 view/copy (no-op for the normal case)."""
     if t.dtype != torch.float32:
         t = t.float()
-    return t if t.is_contiguous() else t.contiguous()
+    t = t if t.is_contiguous() else t.contiguous()
+    if t.data_ptr() % 16 != 0:  # a view with an odd storage offset: the kernels use 16-byte vector accesses
+        t = t.clone()
+    return t
 
 
 def make_grid_list(data: Optional[torch.Tensor], sizes: Sequence[Sequence[int]], channels=None) -> GridList:

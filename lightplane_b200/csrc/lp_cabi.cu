@@ -1,6 +1,7 @@
 // C-ABI entry points of include/lightplane_b200.h: argument validation, kernel-parameter
 // construction (grid tables, MLP layer tables, shared-memory budgeting) and launches.
 // Stateless; everything runs on the caller's stream.
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -47,6 +48,8 @@ static int lp_make_gridset(const lp_grid_list* in, LpGridSet* out, const char* n
   if (in->num_grids < 1 || in->num_grids > LP_MAX_GRIDS)
     LP_FAIL(LP_ERR_INVALID_ARG, "%s: num_grids=%d not in [1,%d]", name, in->num_grids, LP_MAX_GRIDS);
   if (!in->data) LP_FAIL(LP_ERR_INVALID_ARG, "%s: data is NULL", name);
+  if (((uintptr_t)in->data & 15) != 0)  // the kernels read / reduce rows as 16-byte vectors
+    LP_FAIL(LP_ERR_INVALID_ARG, "%s: data is not 16-byte aligned", name);
   out->data = in->data;
   out->n = in->num_grids;
   out->C = in->channels;
@@ -56,6 +59,8 @@ static int lp_make_gridset(const lp_grid_list* in, LpGridSet* out, const char* n
     if (s[0] < 1 || s[1] < 1 || s[2] < 1 || s[3] < 1)
       LP_FAIL(LP_ERR_INVALID_ARG, "%s: grid %d has a non-positive size", name, i);
     if (s[0] != in->sizes[0][0]) LP_FAIL(LP_ERR_INVALID_ARG, "%s: grids differ in batch size", name);
+    if (s[4] != in->channels)
+      LP_FAIL(LP_ERR_INVALID_ARG, "%s: grid %d has %d channels, the list says %d", name, i, s[4], in->channels);
     LpGrid& g = out->g[i];
     g.B = s[0]; g.D = s[1]; g.H = s[2]; g.W = s[3];
     // classification of grid_sample_util.py:1111-1173
@@ -78,6 +83,7 @@ static int lp_make_rays(const lp_rays* in, LpRays* out, int need_enc_dim) {
     if (in->num_rays > 0 && !in->encoding) LP_FAIL(LP_ERR_INVALID_ARG, "rays.encoding is NULL");
     if (in->encoding_dim != need_enc_dim)
       LP_FAIL(LP_ERR_INVALID_ARG, "rays.encoding_dim=%d, expected %d", in->encoding_dim, need_enc_dim);
+    if (((uintptr_t)in->encoding & 15) != 0) LP_FAIL(LP_ERR_INVALID_ARG, "rays.encoding is not 16-byte aligned");
   }
   out->dir = in->directions; out->org = in->origins; out->gidx = in->grid_idx;
   out->near = in->near; out->far = in->far; out->enc = in->encoding;
@@ -464,6 +470,7 @@ int lp_mlp_splat_backward(void* stream, const lp_march_cfg* cfg, const lp_mlp_sp
   if ((rc = lp_make_march(cfg, &M))) return rc;
   if ((rc = lp_make_gridset(input_grid, &IN, "input_grid"))) return rc;
   if ((rc = lp_make_gridset(grad_grid, &GG, "grad_grid"))) return rc;
+  if (IN.g[0].B != GG.g[0].B) LP_FAIL(LP_ERR_INVALID_ARG, "input / gradient grid batch sizes differ");
   if ((rc = lp_make_splat_mlp(spec, IN.C, GG.C, &S))) return rc;
   if ((rc = lp_make_rays(rays, &R, IN.C))) return rc;
   if (R.n == 0) return LP_OK;

@@ -92,6 +92,13 @@ LP_DEVICE float lp_depth(int step, float near, float far, int S, int S_inf, floa
   float n_disp = one_minus_f + d_inf * f;
   return far * (1.f / n_disp);
 }
+// Step length of sample `step`: depth(step) - depth(step-1) as the reference's NAIVE path forms it (depths.diff(),
+// naive_renderer.py:252-257): with S == 1 the depth before the first background sample is depth_0 = near.  (The
+// reference's Triton kernels use `far` there, depth_inv_sphere(..., -1); for S > 1 both agree since depth_{S-1} = far.
+// Like for the background schedule itself -- DESIGN.md section 2 -- this implementation follows the naive semantics.)
+LP_DEVICE float lp_delta(int step, float depth, float near, float far, int S, int S_inf, float d_inf) {
+  return depth - lp_depth(step - 1, near, far, S, S_inf, d_inf);
+}
 
 // MERF contraction then x0.5 (ray_util.py:12-45).
 LP_DEVICE float lp_contract_one(float v, float n) {

@@ -264,7 +264,7 @@ __global__ void lp_render_fwd_generic_kernel(LpRays R, LpMarch M, LpDecoder D, L
   const float* logc = arena + A.yc[D.color.n_layers - 1] * LP_LS;
   for (int step = 0; step < tot; ++step) {
     const float depth = lp_depth(step, s.near, s.far, M.S, M.S_inf, M.disparity_at_inf);
-    const float delta = depth - lp_depth(step - 1, s.near, s.far, M.S, M.S_inf, M.disparity_at_inf);
+    const float delta = lp_delta(step, depth, s.near, s.far, M.S, M.S_inf, M.disparity_at_inf);
     float x = s.ox + depth * s.dx, y = s.oy + depth * s.dy, z = s.oz + depth * s.dz;
     if (M.contract) lp_contract(x, y, z);
     float occ = 1.f;
@@ -365,7 +365,7 @@ __global__ void lp_render_bwd_generic_kernel(LpRays R, LpMarch M, LpDecoder D, L
   const float* logc = arena + A.yc[nc - 1] * LP_LS;
   for (int step = 0; step < tot; ++step) {
     const float depth = lp_depth(step, s.near, s.far, M.S, M.S_inf, M.disparity_at_inf);
-    const float delta = depth - lp_depth(step - 1, s.near, s.far, M.S, M.S_inf, M.disparity_at_inf);
+    const float delta = lp_delta(step, depth, s.near, s.far, M.S, M.S_inf, M.disparity_at_inf);
     float x = s.ox + depth * s.dx, y = s.oy + depth * s.dy, z = s.oz + depth * s.dz;
     if (M.contract) lp_contract(x, y, z);
     float occ = 1.f;

@@ -84,7 +84,8 @@ LP_DEVICE void lp_depth_delta(const Sched& s, float near, float far, float& dept
     delta = depth - ((far - near) * s.prev + near);
   } else {
     depth = far * s.cur;
-    delta = depth - (s.first_inf ? ((far - near) * 1.f + near) : far * s.prev);
+    // depth before the first background sample = the last regular depth: far, or near when S == 1 (naive_renderer.py:252-257)
+    delta = depth - (s.first_inf ? (s.single ? near : (far - near) * 1.f + near) : far * s.prev);
   }
 }
 
@@ -426,13 +427,16 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
                    w_t1h = lp_tc_kdesc_lo(sm + I::T1_HI), w_t1l = lp_tc_kdesc_lo(sm + I::T1_LO),
                    w_och = lp_tc_kdesc_lo(sm + I::OC_HI), w_ocl = lp_tc_kdesc_lo(sm + I::OC_LO);
   unsigned long long* bar = bars + grp;
+  float4* ecb = reinterpret_cast<float4*>(sm + I::FWD_END + 128 + grp * 16384) + (tid % GT);  // float4 [8][128] per group
   int phase = 0;
   const int num_tiles = (R.n + GT - 1) / GT;
   const int tot = M.S + M.S_inf;
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
     const Ray1 me = lp_load_ray1(R, lp_tile_ray(M, tile, tid % GT), G.g[0].B);
-    {  // stage the ray encoding once (columns TC_E..): A operand of the colour layer's second half
+    {  // The ray encoding's share of the colour hidden layer, enc x Wc0 + b, is a per-ray constant: one product per ray
+       // tile (k-steps 2, 3 of the [opacity | colour] tile = the rows the encoding meets), kept in shared memory,
+       // where it stands in for the bias.  (Same arithmetic, in the same order, as the backward kernel's recompute.)
       float e[32];
       const float4* e4 = reinterpret_cast<const float4*>(R.enc + (long long)(me.active ? me.ray : R.n - 1) * H);
 #pragma unroll
@@ -440,7 +444,15 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
         const float4 v = __ldg(e4 + k);
         e[4 * k] = v.x; e[4 * k + 1] = v.y; e[4 * k + 2] = v.z; e[4 * k + 3] = v.w;
       }
-      lp_stage_row<32>(tme + TC_E, e);
+      lp_stage_row<32>(tme + TC_A, e);
+      LP_TCG_HANDOFF(1 + grp, GT, leader, lp_issue_layer_part(tbase, TC_D, TC_A, w_och, w_ocl, 2, 2, 1024, 64, 16, wig); lp_tc_commit(bar));
+      LP_TCG_WAIT(bar, phase);
+      lp_tmem_ld32u(tme + TC_D + 32, e);
+      lp_tmem_zero<32>(tme + TC_D + 32);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        ecb[k * GT] = make_float4(e[4 * k] + F[I::FB + 96 + 4 * k], e[4 * k + 1] + F[I::FB + 97 + 4 * k],
+                                  e[4 * k + 2] + F[I::FB + 98 + 4 * k], e[4 * k + 3] + F[I::FB + 99 + 4 * k]);
     }
     LpCompFwd cf;
     // Empty-space folding.  A sample that misses every grid (or is masked out of bounds) has all-zero features,
@@ -508,31 +520,45 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + 32 + j], 0.f);
       lp_stage_row<32>(tme + TC_A, v);
-      // ---- opacity + colour hidden layers: [trunk | encoding] (K = 64) x [64 outputs] ----
+      // ---- opacity + colour hidden layers: trunk (K = 32) x [64 outputs]; the encoding's share comes from `ecb` ----
       lp_tmem_wait_st();
       lp_tc_fence_before();
       lp_bar_sync(1 + grp, GT);
       if (leader) {
         lp_tc_fence_after();
         lp_issue_layer_part(tbase, TC_D, TC_A, w_och, w_ocl, 2, 0, 1024, 64, 16, wig);
-        lp_issue_layer_part(tbase, TC_D, TC_E, w_och, w_ocl, 2, 2, 1024, 64, 16, wig - 2);
         lp_tc_commit(bar);
       }
       lp_mbar_wait(bar, phase); phase ^= 1;
       lp_tc_fence_after();
-      // ---- output layer (4 wide) on the CUDA cores, exact fp32 ----
-      raw = F[I::FBL + 3]; lg0 = F[I::FBL]; lg1 = F[I::FBL + 1]; lg2 = F[I::FBL + 2];
-      lp_tmem_ld32u(tme + TC_D, v);
-      lp_tmem_zero<32>(tme + TC_D);
+      // ---- output layer (4 wide) on the CUDA cores, exact fp32 (two partial sums per output, as in the backward) ----
+      {
+        float r0 = F[I::FBL + 3], r1 = 0.f;
+        lp_tmem_ld32u(tme + TC_D, v);
+        lp_tmem_zero<32>(tme + TC_D);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) raw = fmaf(fmaxf(v[j] + F[I::FB + 64 + j], 0.f), F[I::FWO + j], raw);
-      lp_tmem_ld32u(tme + TC_D + 32, v);
-      lp_tmem_zero<32>(tme + TC_D + 32);
+        for (int j = 0; j < 32; j += 2) {
+          r0 = fmaf(fmaxf(v[j] + F[I::FB + 64 + j], 0.f), F[I::FWO + j], r0);
+          r1 = fmaf(fmaxf(v[j + 1] + F[I::FB + 64 + j + 1], 0.f), F[I::FWO + j + 1], r1);
+        }
+        raw = r0 + r1;
+        float a0 = F[I::FBL], a1 = F[I::FBL + 1], a2 = F[I::FBL + 2], b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        lp_tmem_ld32u(tme + TC_D + 32, v);
+        lp_tmem_zero<32>(tme + TC_D + 32);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float hc = fmaxf(v[j] + F[I::FB + 96 + j], 0.f);
-        const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
-        lg0 = fmaf(hc, w.x, lg0); lg1 = fmaf(hc, w.y, lg1); lg2 = fmaf(hc, w.z, lg2);
+        for (int k = 0; k < 8; ++k) {
+          const float4 eb = ecb[k * GT];
+          v[4 * k] = fmaxf(v[4 * k] + eb.x, 0.f); v[4 * k + 1] = fmaxf(v[4 * k + 1] + eb.y, 0.f);
+          v[4 * k + 2] = fmaxf(v[4 * k + 2] + eb.z, 0.f); v[4 * k + 3] = fmaxf(v[4 * k + 3] + eb.w, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float4 w0 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
+          const float4 w1 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j + 4);
+          a0 = fmaf(v[j], w0.x, a0); a1 = fmaf(v[j], w0.y, a1); a2 = fmaf(v[j], w0.z, a2);
+          b0 = fmaf(v[j + 1], w1.x, b0); b1 = fmaf(v[j + 1], w1.y, b1); b2 = fmaf(v[j + 1], w1.z, b2);
+        }
+        lg0 = a0 + b0; lg1 = a1 + b1; lg2 = a2 + b2;
       }
       if (probe) { e_raw = raw; e_lg0 = lg0; e_lg1 = lg1; e_lg2 = lg2; continue; }
       } else {
@@ -590,7 +616,7 @@ template <int C, bool SCAF>
 static int lp_tc_render_forward_t(cudaStream_t st, const LpRenderArgs& a, const float* params, float* out_len, float* out_nlt,
                                   float* out_feat, int feat_stride) {
   const int groups = LP_TC_FWD_GROUPS;
-  const size_t bytes = Img<C>::FWD_END + 128;
+  const size_t bytes = Img<C>::FWD_END + 128 + (size_t)groups * 16384;  // weights, mbarriers, per group the rays' enc x Wc0 + b
   if (LP_TC_SET_SMEM((lp_render_fwd_tc_kernel<C, SCAF>), bytes)) return LP_ERR_CUDA;
   const int tiles = (a.R.n + GT - 1) / GT;
   int blocks = (tiles + groups - 1) / groups;

@@ -40,6 +40,13 @@ LP_DEVICE void lp_issue_tf32_part(unsigned tbase, int d_col, int a_col, lp_kdesc
   }
 }
 
+// Precision of the widest input-gradient product [d_ho | d_hc] (K = 64) -> d_t: 0 = three-product bf16 hi+lo form like
+// the recompute (grid gradient ~3e-5 off the fp64 oracle), 1 = one kind::tf32 product (a third fewer MMAs, no hi/lo
+// split of 64 values per sample; measured -1.5 ms on the headline backward, grid gradient 0.6-0.9e-3 off the oracle
+// and the reference's Triton kernels: inside north_star's 1e-3 but without margin, hence not the default).
+#ifndef LP_BWD_XT_TF32
+#define LP_BWD_XT_TF32 0
+#endif
 #ifdef LP_ABL_NO_DW
 #define LP_ABL_DW(x)
 #else
@@ -78,6 +85,7 @@ struct SImg {
   // transposed weights of the input-gradient products:
   static constexpr int XT = (I::FWD_END + 127) / 128 * 128;  // d_t:  tf32 [32 trunk][64: opacity hidden | colour hidden], K-major:
                                                              //       (n, k) at (n/8)*2048 + (k/4)*128 + (n%8)*16 + (k%4)*4
+                                                             //       (LP_BWD_XT_TF32 == 0: bf16 hi at XT, lo at XT + 4096, [32][64] K-major)
   static constexpr int XH_HI = XT + 8192;                    // d_h1: bf16 hi / lo [32][32], K-major as the forward tiles
   static constexpr int XH_LO = XH_HI + 2048;
   static constexpr int X0_HI = XH_LO + 2048;                 // d_x0: bf16 hi / lo [C][32]
@@ -105,7 +113,12 @@ LP_DEVICE void lp_build_simg(unsigned char* sm, const float* __restrict__ P, con
   const int tid = threadIdx.x, nth = blockDim.x;
   for (int e = tid; e < 32 * 64; e += nth) {  // B[n = trunk feature][k]: k < 32 opacity hidden k, else colour hidden k-32
     const int n = e >> 6, k = e & 63;
-    lp_put_w_tf32(sm, W::XT, n, k, 64, k < 32 ? P[o0.w_off + n * o0.N + k] : P[c0.w_off + n * c0.N + (k - 32)]);
+    const float w = k < 32 ? P[o0.w_off + n * o0.N + k] : P[c0.w_off + n * c0.N + (k - 32)];
+#if LP_BWD_XT_TF32
+    lp_put_w_tf32(sm, W::XT, n, k, 64, w);
+#else
+    lp_put_w(sm, W::XT, W::XT + 4096, n, k, 64, w);
+#endif
   }
   for (int e = tid; e < 32 * 32; e += nth) lp_put_w(sm, W::XH_HI, W::XH_LO, e >> 5, e & 31, 32, P[t1.w_off + (e >> 5) * t1.N + (e & 31)]);
   for (int e = tid; e < C * 32; e += nth) lp_put_w(sm, W::X0_HI, W::X0_LO, e >> 5, e & 31, 32, P[t0.w_off + (e >> 5) * t0.N + (e & 31)]);
@@ -301,7 +314,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
     const lp_kdesc_t w_t0h = lp_tc_kdesc_lo(sm + I::T0_HI), w_t0l = lp_tc_kdesc_lo(sm + I::T0_LO),
                      w_t1h = lp_tc_kdesc_lo(sm + I::T1_HI), w_t1l = lp_tc_kdesc_lo(sm + I::T1_LO),
                      w_och = lp_tc_kdesc_lo(sm + I::OC_HI), w_ocl = lp_tc_kdesc_lo(sm + I::OC_LO),
-                     w_xt = lp_tc_kdesc_lo(sm + W::XT), w_xhh = lp_tc_kdesc_lo(sm + W::XH_HI), w_xhl = lp_tc_kdesc_lo(sm + W::XH_LO),
+                     w_xt = lp_tc_kdesc_lo(sm + W::XT), w_xtl = lp_tc_kdesc_lo(sm + W::XT + 4096), w_xhh = lp_tc_kdesc_lo(sm + W::XH_HI), w_xhl = lp_tc_kdesc_lo(sm + W::XH_LO),
                      w_x0h = lp_tc_kdesc_lo(sm + W::X0_HI), w_x0l = lp_tc_kdesc_lo(sm + W::X0_LO);
     int phase = 0, phase0 = 0, n_dw = 0, n_slot = 0, n_dx = 0, n_xt = 0;
 #define LP_ISSUE(A, WH, WL, KS, K0, NS, N, LO, WI) lp_issue_layer_part(tbase, ST_D, A, WH, WL, KS, K0, NS, N, LO, WI)
@@ -442,7 +455,11 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         for (int j = 0; j < 32; ++j) v[j] = g_raw * F[I::FWO + j];  // d_ho
         lp_gate_row<32>(v, gs + W::STK, W::CH_HO, s);
         lp_tile_row<32>(gs + W::DY, 4, s, v);
+#if LP_BWD_XT_TF32
         lp_stage_row_tf32<32>(tme + ST_A, v);
+#else
+        lp_stage_row<32, 32>(tme + ST_A, v);        // [d_ho | d_hc]: packed hi words at columns 0..31, lo at 32..63
+#endif
 #pragma unroll
         for (int j = 0; j < 32; ++j) {                                     // d_hc
           const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
@@ -452,8 +469,13 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
 #pragma unroll
         for (int j = 0; j < 32; ++j) S[j] += v[j];
         lp_tile_row<32>(gs + W::DY, 8, s, v);
+#if LP_BWD_XT_TF32
         lp_stage_row_tf32<32>(tme + ST_A + 32, v);
         LP_TC_ROUND(LP_ISSUE_TF32(ST_D, ST_A, w_xt, 8, 0, 2048, 32); lp_tc_commit(bar));
+#else
+        lp_stage_row<32, 32>(tme + ST_A + 16, v);
+        LP_TC_ROUND(LP_ISSUE(ST_A, w_xt, w_xtl, 4, 0, 1024, 32, 32, wi); lp_tc_commit(bar));
+#endif
         lp_tmem_ld<32>(tme + ST_D, v);
         lp_tmem_zero<32>(tme + ST_D);
         lp_gate_row<32>(v, gs + W::STK, W::CH_TR, s);  // d_t
@@ -482,9 +504,17 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         }
         lp_tile_row<32>(gs + W::STK, W::CH_H1, s, v);
         lp_tile_row<32>(gs + W::DY, 8, s, S);
+#if LP_BWD_XT_TF32
         lp_stage_row_tf32<32>(tme + ST_A + 32, S);  // K index 32..63 of the d_t weight tile = colour hidden
+#else
+        lp_stage_row<32, 32>(tme + ST_A, S);        // issued against k-steps 2, 3 of the tile (K index 32..63 = colour hidden)
+#endif
         lp_fence_async_smem();
+#if LP_BWD_XT_TF32
         LP_TC_ROUND(LP_ISSUE_TF32(ST_D, ST_A + 32, w_xt, 4, 4, 2048, 32); lp_tc_commit(bar);
+#else
+        LP_TC_ROUND(LP_ISSUE(ST_A, w_xt, w_xtl, 2, 2, 1024, 32, 32, wi); lp_tc_commit(bar);
+#endif
                     lp_ws_issue_encw_part<C>(tmem, gs, wi); lp_tc_commit(bar_dw));
         ++n_dw;
         lp_tmem_ld<32>(tme + ST_D, v);

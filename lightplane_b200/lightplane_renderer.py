@@ -29,28 +29,31 @@ from .mlp_utils import MIN_BLOCK_SIZE, DecoderParams, get_triton_function_input_
 # Opt-in device-side validation (costs host syncs, like the reference's asserts).
 VALIDATE_INPUTS = False
 
+import weakref
+
+# id(tensor) -> (weakref to the tensor, _version, dims): an entry is valid only while the SAME tensor object is alive and
+# unmodified, so a recycled address or id can never serve another decoder's dims.
 _DIMS_CACHE: dict = {}
 
 
+def _tensor_dims(t: torch.Tensor) -> List[int]:
+    """`t.tolist()` as ints.  CPU tensors are read directly; device tensors are read back once per tensor object and
+    version (the reference `.item()`s them every call, lightplane_renderer.py:221-233)."""
+    if t.device.type == "cpu":
+        return [int(v) for v in t.tolist()]
+    ent = _DIMS_CACHE.get(id(t))
+    if ent is not None and ent[0]() is t and ent[1] == t._version:
+        return ent[2]
+    dims = [int(v) for v in t.tolist()]
+    key = id(t)
+    _DIMS_CACHE[key] = (weakref.ref(t, lambda _r, k=key: _DIMS_CACHE.pop(k, None)), t._version, dims)
+    return dims
+
+
 def _decoder_dims(dp: DecoderParams):
-    """Host copy of the decoder layer dims, cached so that device-resident `n_hidden_*`
-    buffers are read back at most once (the reference `.item()`s them every call, :221-233)."""
-    key = tuple(
-        (t.data_ptr(), t._version, t.numel(), str(t.device))
-        for t in (dp.n_hidden_trunk, dp.n_hidden_opacity, dp.n_hidden_color)
-    )
-    hit = _DIMS_CACHE.get(key)
-    if hit is None:
-        if len(_DIMS_CACHE) > 256:
-            _DIMS_CACHE.clear()
-        hit = (
-            get_triton_function_input_dims(dp.n_hidden_trunk, dp.n_hidden_opacity, dp.n_hidden_color),
-            [int(v) for v in dp.n_hidden_trunk.tolist()],
-            [int(v) for v in dp.n_hidden_opacity.tolist()],
-            [int(v) for v in dp.n_hidden_color.tolist()],
-        )
-        _DIMS_CACHE[key] = hit
-    return hit
+    """Host copy of the decoder layer dims: `(triton-style dims, n_hidden_trunk, n_hidden_opacity, n_hidden_color)`."""
+    nt, no, nc = (_tensor_dims(t) for t in (dp.n_hidden_trunk, dp.n_hidden_opacity, dp.n_hidden_color))
+    return get_triton_function_input_dims(nt, no, nc), nt, no, nc
 
 
 def _mlp_numel(d_in, d_hid, d_out, n_layers) -> int:

@@ -17,7 +17,7 @@ import torch
 
 from .lightplane_renderer import lightplane_renderer
 from .misc_utils import if_not_none_else, process_and_flatten_grid
-from .mlp_utils import DecoderParams, init_decoder_params
+from .mlp_utils import DecoderParams, flattened_decoder_params_to_list, init_decoder_params
 from .ray_utils import Rays, calc_harmonic_embedding, calc_harmonic_embedding_dim, jitter_near_far
 
 logger = logging.getLogger(__name__)
@@ -252,35 +252,51 @@ class LightplaneRenderer(torch.nn.Module):
         )
 
     # ------------------------------------------------------------------------------------
-    @torch.no_grad()
+    def get_decoder_params_list(self):
+        """`(weights_trunk, biases_trunk, weights_opacity, biases_opacity, weights_color, biases_color)`:
+        the weight matrices / bias vectors inside `mlp_params` (renderer_module.py:255-284)."""
+        return flattened_decoder_params_to_list(self.mlp_params, *self._n_hidden)
+
+    def _points_as_rays(self, pts, pts_to_grid_idx, encoding):
+        """Evaluation points as degenerate rays for the ray-march kernels: zero direction, origin = the point, so every
+        sample of the "ray" is the point itself.  `pts` is `[n_rays, n_pts, 3]` with `pts_to_grid_idx [n_rays]` (the
+        reference's layout) or flat `[P, 3]` with `[P]`."""
+        if pts.ndim == 3:
+            n_rays, n_pts, dim = pts.shape
+            assert dim == 3 and tuple(pts_to_grid_idx.shape) == (n_rays,)
+            flat = pts.reshape(-1, 3)
+            idx = pts_to_grid_idx.repeat_interleave(n_pts)
+            if encoding is not None:
+                encoding = encoding.repeat_interleave(n_pts, dim=0)
+            shape = (n_rays, n_pts)
+        else:
+            assert pts.ndim == 2 and pts.shape[1] == 3 and tuple(pts_to_grid_idx.shape) == (pts.shape[0],)
+            flat, idx, shape = pts, pts_to_grid_idx, (pts.shape[0],)
+        n = flat.shape[0]
+        if encoding is None:
+            encoding = flat.new_zeros(n, self.rays_encoding_dim)
+        rays = Rays(directions=torch.zeros_like(flat), origins=flat.contiguous(), grid_idx=idx.to(torch.int32),
+                    near=flat.new_zeros(n), far=flat.new_ones(n), encoding=encoding)
+        return rays, shape
+
     def eval_opacity_at_points(
         self,
-        pts: torch.Tensor,  # [P, 3] in [-1, 1]
-        pts_to_grid_idx: torch.Tensor,  # [P]
+        pts: torch.Tensor,  # [n_rays, n_pts, 3]
+        pts_to_grid_idx: torch.Tensor,  # [n_rays]
         feature_grid,
         scaffold: Optional[torch.Tensor] = None,
         gain: Optional[float] = None,
         mask_out_of_bounds_samples: Optional[bool] = None,
-        contract_coords: Optional[bool] = None,
         grid_sizes=None,
+        contract_coords: Optional[bool] = None,
     ) -> torch.Tensor:
-        """`gain * softplus(opacity_raw)` at 3-D points, evaluated THROUGH the ray-march kernel:
-        each point becomes a zero-direction ray with near=0, far=1 and two samples, whose
-        negative log transmittance is `2 * gain * opacity` (delta = 1 for both samples).
-        The reference evaluates this with its naive PyTorch decoder (renderer_module.py:258-346)."""
-        n = pts.shape[0]
-        zeros = pts.new_zeros(n)
-        color_grid = None
-        if self.n_hidden_trunk.numel() == 0:  # colour-grid mode: colours are irrelevant here
-            color_grid = feature_grid
-        rays = Rays(
-            directions=torch.zeros_like(pts),
-            origins=pts.contiguous(),
-            grid_idx=pts_to_grid_idx.to(torch.int32),
-            near=zeros,
-            far=zeros + 1.0,
-            encoding=pts.new_zeros(n, self.rays_encoding_dim),
-        )
+        """`gain * softplus(opacity_raw)` (times the scaffold's occupancy) at 3-D points, `[n_rays, n_pts]`
+        (renderer_module.py:302-346; flat `[P,3]` / `[P]` inputs are accepted too and give `[P]`).
+        The reference evaluates this with its naive PyTorch decoder; here it goes THROUGH the ray-march kernel: each
+        point is a zero-direction ray with near=0, far=1 and two samples (delta = 1 for both), whose negative log
+        transmittance is `2 * gain * opacity`."""
+        color_grid = feature_grid if self.n_hidden_trunk.numel() == 0 else None  # colour-grid mode: colours are irrelevant here
+        rays, shape = self._points_as_rays(pts, pts_to_grid_idx, None)
         _, nlt, _ = lightplane_renderer(
             rays,
             feature_grid,
@@ -290,13 +306,60 @@ class LightplaneRenderer(torch.nn.Module):
             mask_out_of_bounds_samples=if_not_none_else(
                 mask_out_of_bounds_samples, self.mask_out_of_bounds_samples
             ),
-            contract_coords=if_not_none_else(contract_coords, self.contract_coords),
+            contract_coords=bool(contract_coords) if contract_coords is not None else False,
             scaffold=scaffold,
             color_grid=color_grid,
             grid_sizes=grid_sizes,
             color_grid_sizes=grid_sizes if color_grid is not None else None,
         )
-        return 0.5 * nlt
+        return (0.5 * nlt).reshape(shape)
+
+    def eval_decoder_at_points(
+        self,
+        pts: torch.Tensor,  # [n_rays, n_pts, 3]
+        pts_to_grid_idx: torch.Tensor,  # [n_rays]
+        rays_encoding: Optional[torch.Tensor],  # [n_rays, rays_encoding_dim]
+        feature_grid,
+        color_feature_grid=None,
+        scaffold: Optional[torch.Tensor] = None,
+        gain: Optional[float] = None,
+        mask_out_of_bounds_samples: Optional[bool] = None,
+        contract_coords: Optional[bool] = None,
+        directions: Optional[torch.Tensor] = None,
+    ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Decoder outputs at 3-D points (renderer_module.py:183-253): `opacity [n_rays, n_pts]` = gain * softplus(raw)
+        and `features [n_rays, n_pts, chn]` = sigmoid(colour logits), both times the scaffold's occupancy; `chn` is the
+        width of the colour layer in the parameter layout (zero-padded to 16: padded channels read sigmoid(0) = 0.5, as
+        in the reference).  Evaluated THROUGH the ray-march kernels on degenerate rays (see `eval_opacity_at_points`):
+        the opacity from a two-sample march; the colours from a one-sample march with a saturating gain (render weight
+        1 - exp(-gain * softplus(raw)) == 1 in fp32), which makes the rendered feature the decoder's colour."""
+        n_rays = pts.shape[0]
+        assert pts.ndim == 3 and pts.shape[2] == 3 and tuple(pts_to_grid_idx.shape) == (n_rays,)
+        if rays_encoding is not None:
+            assert tuple(rays_encoding.shape) == (n_rays, self.rays_encoding_dim)
+        else:
+            assert directions is not None, "Must pass one of (rays_encoding, directions)"
+            assert tuple(directions.shape) == (n_rays, 3)
+        enc = self._get_ray_encoding(rays_encoding, directions)
+        mask_oob = if_not_none_else(mask_out_of_bounds_samples, self.mask_out_of_bounds_samples)
+        contract = if_not_none_else(contract_coords, self.contract_coords)
+        rays, shape = self._points_as_rays(pts, pts_to_grid_idx, enc)
+        common = dict(mask_out_of_bounds_samples=mask_oob, contract_coords=contract, scaffold=scaffold,
+                      color_grid=color_feature_grid)
+        _, nlt, _ = lightplane_renderer(rays, feature_grid, self.get_decoder_params(), num_samples=2,
+                                        gain=if_not_none_else(gain, self.gain), **common)
+        _, _, col = lightplane_renderer(rays, feature_grid, self.get_decoder_params(), num_samples=1, gain=3.0e38, **common)
+        opacity = (0.5 * nlt).reshape(shape)
+        chn = int(self.n_hidden_color[-1])
+        if chn > col.shape[1]:  # the layout's padded colour channels: zero weights and biases -> sigmoid(0), times the occupancy
+            pad = col.new_full((col.shape[0], chn - col.shape[1]), 0.5)
+            if scaffold is not None:
+                p = rays.origins
+                if contract:
+                    p = _contract_points(p)
+                pad = pad * _nearest_occupancy(scaffold, p, rays.grid_idx.long())[:, None]
+            col = torch.cat([col, pad], dim=1)
+        return opacity, col.reshape(*shape, chn)
 
     @torch.no_grad()
     def calculate_scaffold(
@@ -320,7 +383,8 @@ class LightplaneRenderer(torch.nn.Module):
         for b in range(B):
             idx = torch.full((pts.shape[0],), b, device=device, dtype=torch.int32)
             occ[b] = self.eval_opacity_at_points(
-                pts, idx, feature_grid, scaffold=None, grid_sizes=grid_sizes
+                pts, idx, feature_grid, scaffold=None, gain=self.gain,
+                mask_out_of_bounds_samples=self.mask_out_of_bounds_samples, grid_sizes=grid_sizes,
             ).reshape(D, H, W)
         if dilate_scaffold > 0:
             k = 2 * dilate_scaffold + 1
@@ -373,3 +437,23 @@ def _check_renderer_ray_encoding_input(
         " rays.encoding=None) or supply your own [n_rays, ray_encoding_dim] rays.encoding and"
         " set ray_embedding_num_harmonics=None."
     )
+
+
+def _contract_points(p: torch.Tensor) -> torch.Tensor:
+    """MERF contraction then x0.5 (ray_util.py:12-45), for the host-side occupancy lookup of `eval_decoder_at_points`."""
+    a = p.abs()
+    n = a.max(dim=-1, keepdim=True).values
+    scaled = p / n.clamp_min(1e-12)
+    out = torch.where(n > 1, torch.where((a - n).abs() <= 1e-8, (2 - 1 / a.clamp_min(1e-12)) * (p / a.clamp_min(1e-12)), scaled), p)
+    return 0.5 * out
+
+
+def _nearest_occupancy(scaffold: torch.Tensor, p: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """Nearest-cell value of a `[B,D,H,W]` scaffold at points `p [P,3]` (x->W, y->H, z->D, align_corners=False), zero
+    outside the grid and outside [-1,1]^3 (grid_sample_util.py:717-777)."""
+    B, D, H, W = scaffold.shape
+    size = p.new_tensor([W, H, D])
+    i = torch.floor(((p + 1) * 0.5) * size - 0.5 + 0.5)
+    ok = ((i >= 0) & (i < size)).all(-1) & (p.abs() <= 1).all(-1)
+    i = i.clamp_min(0).minimum(size - 1).long()
+    return scaffold[idx, i[:, 2], i[:, 1], i[:, 0]] * ok.to(scaffold.dtype)

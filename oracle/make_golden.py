@@ -208,8 +208,71 @@ def run_splatter_case(name, *, n_rays, size, triplane, feat_dim, num_samples, nu
     print("wrote", name)
 
 
+def run_module_case(name, *, n_side, size, triplane, hidden, num_samples, scaffold_res, seed=0, **mod_kw):
+    """Fixtures from the reference's `LightplaneRenderer` MODULE (renderer_module.py), naive implementation on CPU:
+    forward (harmonic ray embedding + Linear, background colour, alpha), `calculate_scaffold`,
+    `eval_opacity_at_points`, `eval_decoder_at_points`, `get_decoder_params_list`."""
+    torch.manual_seed(seed)
+    B, C = size[0], size[4]
+    m = ref.LightplaneRenderer(num_samples=num_samples, color_chn=3, grid_chn=C, mlp_hidden_chn=hidden,
+                               opacity_init_bias=-1.0, use_naive_impl=True, **mod_kw)
+    with torch.no_grad():
+        m.mlp_params.add_(0.05 * torch.randn_like(m.mlp_params))
+    shapes = grid_shapes(size, triplane)
+    grids = [torch.randn(s) for s in shapes]
+    n = n_side * n_side
+    ys, xs = torch.meshgrid(torch.linspace(-0.5, 0.5, n_side), torch.linspace(-0.5, 0.5, n_side), indexing="ij")
+    d = torch.stack([xs, ys, -torch.ones_like(xs)], -1).reshape(-1, 3)
+    o = torch.tensor([0.1, -0.05, 2.2]).expand(n, 3).contiguous()
+    near, far = torch.full((n,), 1.0), torch.full((n,), 3.4)
+    gi = (torch.arange(n) * B // n).long()
+    rays = ref.Rays(directions=d, origins=o, grid_idx=gi, near=near, far=far)
+    length, alpha, feat = m(rays, grids)
+    # threshold = the median opacity over the lattice, so that about half of the cells survive before the dilation
+    lin = torch.linspace(-1, 1, scaffold_res)
+    lat = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), -1).reshape(1, -1, 3)
+    thr = float(m.eval_opacity_at_points(lat, torch.zeros(1, dtype=torch.long), grids).median())
+    scaffold = m.calculate_scaffold(grids, [B, scaffold_res, scaffold_res, scaffold_res], "cpu", threshold=thr, dilate_scaffold=0)
+    length_s, alpha_s, feat_s = m(rays, grids, scaffold=scaffold)
+    g = torch.Generator().manual_seed(seed + 1)
+    pts = torch.rand(12, 7, 3, generator=g) * 2.4 - 1.2
+    pidx = torch.randint(0, B, (12,), generator=g)
+    pdirs = torch.randn(12, 3, generator=g)
+    opa = m.eval_opacity_at_points(pts, pidx, grids)
+    opa2, col2 = m.eval_decoder_at_points(pts, pidx, None, grids, directions=pdirs)
+    opa3, col3 = m.eval_decoder_at_points(pts, pidx, None, grids, scaffold=scaffold, directions=pdirs)
+    plist = m.get_decoder_params_list()
+    data = dict(
+        directions=d, origins=o, grid_idx=gi.int(), near=near, far=far,
+        grid=torch.cat([x.reshape(-1, C) for x in grids], 0), grid_sizes=np.array(shapes, dtype=np.int32),
+        mlp_params=m.mlp_params.detach(), lin_w=m.harmonic_ray_embedding_linear.weight.detach(),
+        lin_b=m.harmonic_ray_embedding_linear.bias.detach(), bg_color=m.bg_color,
+        cfg=np.array([num_samples, hidden, scaffold_res, int(triplane)], dtype=np.int64), scaffold_threshold=np.float64(thr),
+        out_length=length.detach(), out_alpha=alpha.detach(), out_features=feat.detach(),
+        scaffold=scaffold, outs_length=length_s.detach(), outs_alpha=alpha_s.detach(), outs_features=feat_s.detach(),
+        pts=pts, pts_idx=pidx.int(), pts_dirs=pdirs, pts_opacity=opa.detach(),
+        dec_opacity=opa2.detach(), dec_features=col2.detach(), decs_opacity=opa3.detach(), decs_features=col3.detach(),
+        plist_shapes=np.array([[len(grp)] + [int(np.prod(t.shape)) for t in grp] + [0] * (4 - len(grp)) for grp in plist], dtype=np.int64),
+        plist_flat=torch.cat([t.reshape(-1) for grp in plist for t in grp]).detach(),
+    )
+    for k, v in mod_kw.items():
+        data["kw_" + k] = np.array(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                        **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in data.items()})
+    print("wrote", name, "scaffold occupancy", float(scaffold.mean()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--modules-only" not in sys.argv:
+        main_ops()
+    run_module_case("module_triplane_bg", n_side=12, size=(2, 10, 10, 10, 16), triplane=True, hidden=32, num_samples=24,
+                    scaffold_res=10, seed=21, bg_color=(0.1, 0.5, 0.9), gain=2.0, mask_out_of_bounds_samples=True)
+    run_module_case("module_voxel_logT", n_side=10, size=(1, 8, 8, 8, 16), triplane=False, hidden=32, num_samples=16,
+                    scaffold_res=8, seed=22, bg_color=0.25, return_log_transmittance=True, ray_embedding_num_harmonics=2)
+
+
+def main_ops():
     V = (2, 6, 5, 4, 16)
     # renderer: voxel / triplane / every optional feature at least once
     run_renderer_case("render_voxel_222", n_rays=32, size=V, triplane=False, layers=(2, 2, 2),

@@ -137,3 +137,15 @@ def test_hostsim_renderer_tile_walk_hint(lib):
     b = render_case(lib, c, "cpu", ray_image_width=16)
     for k in a:
         assert rel_err(a[k], b[k]) < (1e-4 if k != "g_mlp" else 2e-3), (k, rel_err(a[k], b[k]))
+
+
+@pytest.mark.parametrize("hidden", [32, 16])
+def test_hostsim_single_sample_with_background_samples(lib, hidden):
+    """num_samples == 1 with num_samples_inf > 0: the first background sample's step length is measured from `far`
+    (depth_inv_sphere(..., -1) == far), on the tensor-core path (hidden 32) and on the generic path (hidden 16)."""
+    c = synthetic_case(n=64, C=16, hidden=hidden, layers=(2, 2, 2), color_grid=False, samples=1, samples_inf=3)
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cpu")
+    for k, v in got.items():
+        tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
+        assert rel_err(v, want[k]) < tol, (hidden, k, rel_err(v, want[k]))
