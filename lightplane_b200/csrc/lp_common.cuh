@@ -215,7 +215,9 @@ LP_DEVICE int lp_taps(const LpGrid& g, int C, int b, float x, float y, float z, 
 }
 
 // Nearest-neighbour lookup of a 1-channel voxel grid with zero padding and an additional
-// in-bounds mask (scaffold; grid_sample_util.py:717-777 with round(x) = floor(x + 0.5)).
+// in-bounds mask (scaffold).  Rounding: to nearest, ties to even, as `F.grid_sample(mode="nearest")` of the reference's
+// naive path (naive_renderer.py:568-589); its Triton kernels round ties up (floor(x + 0.5), grid_sample_util.py:717-777) --
+// the two differ only for coordinates exactly half-way between two cells.
 LP_DEVICE float lp_nearest(const LpGridSet& s, int b, float x, float y, float z) {
   const LpGrid& g = s.g[0];
   float ix = ((x + 1.f) * 0.5f) * (float)g.W - 0.5f;
@@ -224,7 +226,7 @@ LP_DEVICE float lp_nearest(const LpGridSet& s, int b, float x, float y, float z)
   if (g.W <= 1) ix = 0.f;
   if (g.H <= 1) iy = 0.f;
   if (g.D <= 1) iz = 0.f;
-  ix = floorf(ix + 0.5f); iy = floorf(iy + 0.5f); iz = floorf(iz + 0.5f);
+  ix = rintf(ix); iy = rintf(iy); iz = rintf(iz);
   bool ok = ix >= 0.f && ix < (float)g.W && iy >= 0.f && iy < (float)g.H && iz >= 0.f && iz < (float)g.D;
   if (!ok) return 0.f;
   long long o = g.base + (((long long)b * g.D + (int)iz) * g.H + (int)iy) * g.W + (int)ix;

@@ -212,13 +212,16 @@ LP_DEVICE void lp_corner_i(int i0, float frac, int size, float& w0, float& w1, i
   c0 = min(max(i0, 0), size - 1);
   c1 = min(max(i0 + 1, 0), size - 1);
 }
-LP_DEVICE int lp_taps_i32(const LpGrid& g, int C, int b, float x, float y, float z, int* off, float* w) {
+// `key` (optional): identity of the sample's footprint on this grid -- the index of its (unclamped) base cell in the grid
+// padded by two cells per axis, batch included: two samples get the same taps iff their keys are equal
+LP_DEVICE int lp_taps_i32(const LpGrid& g, int C, int b, float x, float y, float z, int* off, float* w, int* key = nullptr) {
   if (g.kind == LP_VOXEL) {
     int x0, y0, z0, cx[2], cy[2], cz[2];
     float fx, fy, fz, wx[2], wy[2], wz[2];
     lp_axis_i(x, g.W, x0, fx); lp_axis_i(y, g.H, y0, fy); lp_axis_i(z, g.D, z0, fz);
     if ((unsigned)(x0 + 1) > (unsigned)g.W || (unsigned)(y0 + 1) > (unsigned)g.H || (unsigned)(z0 + 1) > (unsigned)g.D)
       return 0;  // no corner inside the grid: every tap weight is zero
+    if (key) *key = ((b * (g.D + 3) + z0 + 2) * (g.H + 3) + y0 + 2) * (g.W + 3) + x0 + 2;
     lp_corner_i(x0, fx, g.W, wx[0], wx[1], cx[0], cx[1]);
     lp_corner_i(y0, fy, g.H, wy[0], wy[1], cy[0], cy[1]);
     lp_corner_i(z0, fz, g.D, wz[0], wz[1], cz[0], cz[1]);
@@ -239,6 +242,7 @@ LP_DEVICE int lp_taps_i32(const LpGrid& g, int C, int b, float x, float y, float
   float fu, fv, wu[2], wv[2];
   lp_axis_i(u, U, u0, fu); lp_axis_i(v, V, v0, fv);
   if ((unsigned)(u0 + 1) > (unsigned)U || (unsigned)(v0 + 1) > (unsigned)V) return 0;  // the sample misses this plane
+  if (key) *key = (b * (V + 3) + v0 + 2) * (U + 3) + u0 + 2;
   lp_corner_i(u0, fu, U, wu[0], wu[1], cu[0], cu[1]);
   lp_corner_i(v0, fv, V, wv[0], wv[1], cv[0], cv[1]);
   const int bbase = (int)g.base + b * U * V * C;
@@ -695,6 +699,115 @@ LP_DEVICE void lp_splat_regs(const LpGridSet& G, float* grad, int b, float x, fl
         for (int k = 0; k < CW / 4; ++k)
           lp_red_add4_if(on, grad + off[tp] + ch0 + 4 * k, w[tp] * d[4 * k], w[tp] * d[4 * k + 1], w[tp] * d[4 * k + 2],
                          w[tp] * d[4 * k + 3]);
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// Quad-transposed, footprint-merging scatter (the backward kernel's memory warps).
+//
+// A texel row is C floats = 4 x (C/4) contiguous floats.  With one thread per sample every `red.global.add.v4` of a
+// warp touches 32 different rows, 16 bytes each: 32 partial sectors per instruction, and the L2 reduction rate
+// (requests, not bytes) bounds the whole backward (profiles/ncu_r2b_bwd.md: ~1.1 reduced words / clock / SM).  Here
+// the four lanes of a quad (four consecutive rays) first transpose their gradient rows, so that lane q holds channels
+// [q*C/4, (q+1)*C/4) of all four samples; a tap is then ONE contiguous row per quad (full sectors, a quarter of the
+// requests), and samples of the quad that share a bilinear footprint on a plane -- neighbouring pixels mostly do --
+// are summed in registers first and reduced once (reference: grid_sample_util.py:40-99 issues one atomic per sample,
+// tap and channel).  Warp-collective: all 32 lanes call it; `valid` says whether this lane's sample contributes.
+// -------------------------------------------------------------------------------------------------------------------
+template <int CW>
+LP_DEVICE void lp_quad_transpose(float (&blk)[4][CW], int q) {
+  // in: blk[k] = channel block k of MY sample; out: blk[j] = MY channel block (q) of the quad's sample j
+#pragma unroll
+  for (int k0 = 0; k0 < 4; k0 += 2) {  // round 1, partner lane ^ 1: the pair (k0, k0+1)
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      const float send = (q & 1) ? blk[k0][i] : blk[k0 + 1][i];
+      const float recv = __shfl_xor_sync(LP_FULL_MASK, send, 1);
+      if (q & 1) blk[k0][i] = recv; else blk[k0 + 1][i] = recv;
+    }
+  }
+#pragma unroll
+  for (int k0 = 0; k0 < 2; ++k0) {     // round 2, partner lane ^ 2: the pair (k0, k0+2)
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      const float send = (q & 2) ? blk[k0][i] : blk[k0 + 2][i];
+      const float recv = __shfl_xor_sync(LP_FULL_MASK, send, 2);
+      if (q & 2) blk[k0][i] = recv; else blk[k0 + 2][i] = recv;
+    }
+  }
+}
+template <int CW>
+LP_DEVICE void lp_red_row(float* p, const float (&v)[CW]) {
+#pragma unroll
+  for (int k = 0; k < CW / 4; ++k) lp_red_add4(p + 4 * k, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+template <int C>
+LP_DEVICE void lp_splat_quad(const LpGridSet& G, float* grad, int b, float x, float y, float z, bool valid, const float (&d)[C]) {
+  constexpr int CW = C / 4;
+  const int lane = threadIdx.x & 31, q = lane & 3, qbase = lane & ~3;
+  float blk[4][CW];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < CW; ++i) blk[k][i] = valid ? d[k * CW + i] : 0.f;
+  lp_quad_transpose<CW>(blk, q);
+  for (int gi = 0; gi < G.n; ++gi) {
+    int off[8];
+    float w[8];
+    int fkey = -1;
+    const int nt = valid ? lp_taps_i32(G.g[gi], C, b, x, y, z, off, w, &fkey) : 0;
+    if (!__any_sync(LP_FULL_MASK, nt != 0)) continue;  // nobody in the warp touches this grid
+    if (nt == 0) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { off[t] = 0; w[t] = 0.f; }
+    }
+    const int ntw = G.g[gi].kind == LP_VOXEL ? 8 : 4;  // uniform: taps of this grid
+    const int key = nt != 0 ? fkey : -1;  // -1: no contribution
+    int kA = max(key, __shfl_xor_sync(LP_FULL_MASK, key, 1));
+    kA = max(kA, __shfl_xor_sync(LP_FULL_MASK, kA, 2));
+    const bool inA = key >= 0 && key == kA;  // merged pass: every sample of the quad standing on footprint kA
+    const unsigned mA = (__ballot_sync(LP_FULL_MASK, inA) >> qbase) & 15u;
+    if (__any_sync(LP_FULL_MASK, mA != 0)) {
+      const int owner = qbase + (mA ? __ffs((int)mA) - 1 : 0);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        if (t < ntw) {
+          const int o = __shfl_sync(LP_FULL_MASK, off[t], owner);
+          float v[CW];
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float wj = __shfl_sync(LP_FULL_MASK, inA ? w[t] : 0.f, qbase + j);
+#pragma unroll
+            for (int i = 0; i < CW; ++i) v[i] = fmaf(wj, blk[j][i], v[i]);
+          }
+          if (mA) lp_red_row<CW>(grad + o + q * CW, v);
+        }
+      }
+    }
+    // samples of the quad on another footprint: one pass each (rare for neighbouring pixels)
+    const bool left = key >= 0 && !inA;
+    const unsigned mL = __ballot_sync(LP_FULL_MASK, left);
+    if (mL == 0) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!((mL >> j) & 0x11111111u)) continue;  // no quad has a leftover in position j
+      const bool need = (mL >> (qbase + j)) & 1u;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        if (t < ntw) {
+          const int o = __shfl_sync(LP_FULL_MASK, off[t], qbase + j);
+          const float wj = __shfl_sync(LP_FULL_MASK, w[t], qbase + j);
+          if (need) {
+            float v[CW];
+#pragma unroll
+            for (int i = 0; i < CW; ++i) v[i] = wj * blk[j][i];
+            lp_red_row<CW>(grad + o + q * CW, v);
+          }
+        }
       }
     }
   }

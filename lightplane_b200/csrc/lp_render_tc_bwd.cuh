@@ -232,10 +232,10 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         lp_tmem_wait_st();
         lp_tc_fence_before();
         lp_mbar_arrive(dx_free);
-        if (scatter && me.active && prev.oob != 0.f) {
+        if (scatter) {  // (warp-uniform) quad-transposed, footprint-merging reduction into the grid gradient
 #pragma unroll
           for (int c = 0; c < C; ++c) dxp[c] *= prev.oob;
-          lp_splat_regs<C>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, dxp);
+          lp_splat_quad<C>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, me.active && prev.oob != 0.f, dxp);
         }
       };
       // publish one slot: operand row (full slots) into tensor memory, flag + occupancy into shared memory

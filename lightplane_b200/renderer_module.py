@@ -453,7 +453,7 @@ def _nearest_occupancy(scaffold: torch.Tensor, p: torch.Tensor, idx: torch.Tenso
     outside the grid and outside [-1,1]^3 (grid_sample_util.py:717-777)."""
     B, D, H, W = scaffold.shape
     size = p.new_tensor([W, H, D])
-    i = torch.floor(((p + 1) * 0.5) * size - 0.5 + 0.5)
+    i = torch.round(((p + 1) * 0.5) * size - 0.5)  # ties to even, as F.grid_sample(mode="nearest")
     ok = ((i >= 0) & (i < size)).all(-1) & (p.abs() <= 1).all(-1)
     i = i.clamp_min(0).minimum(size - 1).long()
     return scaffold[idx, i[:, 2], i[:, 1], i[:, 0]] * ok.to(scaffold.dtype)

@@ -182,6 +182,7 @@ static inline int __reduce_max_sync(unsigned, int v) {
   for (int d = 16; d > 0; d >>= 1) { int o = lp_hs_exchange(m, lp_hostsim::g_ctx->lane ^ d); m = o > m ? o : m; }
   return m;
 }
+static inline int __ffs(int x) { return x ? __builtin_ffs(x) : 0; }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
 

@@ -67,7 +67,7 @@ def test_renderer_module_vs_reference_module(name):
     for got, key in ((length, "outs_length"), (alpha, "outs_alpha"), (feat, "outs_features")):
         assert rel_err(got, c[key]) < 2e-4, (name, key, rel_err(got, c[key]))
     # point evaluations, the reference's [n_rays, n_pts, 3] layout
-    pts, pidx, pdirs = f("pts"), c["pts_idx"].to(dev).long(), f("pts_dirs")
+    pts, pidx, pdirs = f("pts"), torch.as_tensor(c["pts_idx"]).to(dev).long(), f("pts_dirs")
     opa = m.eval_opacity_at_points(pts, pidx, grids)
     assert opa.shape == c["pts_opacity"].shape and rel_err(opa, c["pts_opacity"]) < 2e-4
     opa2, col2 = m.eval_decoder_at_points(pts, pidx, None, grids, directions=pdirs)
