@@ -146,6 +146,17 @@ LP_DEVICE void lp_ws_issue_encw_part(unsigned tmem, unsigned char* gs, int wi) {
   }
 }
 
+// Code-size switches (headline backward, 16x8 tile walk; profiles/bench_r2_ablation.md):
+//   LP_MLP_COMPACT      1: the two trunk layers / the two last gradient layers are run-time loops of one body each and the
+//                       compositing gradient has one call site: -2.5 ms (decoder warps were 30 % instruction-fetch stalled)
+//   LP_MEM_SINGLE_LOOP  1: one slot loop with single gather / stage / scatter sites in the memory role: +5 ms -- the
+//                       compiler's unrolling of the step loop overlaps one slot's scatter with the next slot's gather
+#ifndef LP_MLP_COMPACT
+#define LP_MLP_COMPACT 1
+#endif
+#ifndef LP_MEM_SINGLE_LOOP
+#define LP_MEM_SINGLE_LOOP 0
+#endif
 #ifndef LP_WS_REGS_MLP
 #define LP_WS_REGS_MLP 168
 #define LP_WS_REGS_MEM 88
@@ -214,6 +225,90 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
     // =================================================================================================================
     // memory group
     // =================================================================================================================
+#if LP_MEM_SINGLE_LOOP
+    LP_SETMAXNREG_DEC(LP_WS_REGS_MEM);
+    int n_slot = 0, n_dw = 0, n_dx = 0;  // slots staged; dW GEMMs the decoder group has issued; d_x0 rows consumed
+    for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
+      const Ray1 me = lp_load_ray1(R, lp_tile_ray(M, tile, s), G.g[0].B);
+      struct Pos { float x, y, z, oob; };
+      Pos prev = {0.f, 0.f, 0.f, 0.f};
+      bool pend = false, pend_scatter = false, any_empty = false;  // a full slot whose d_x0 is still to be consumed / scattered
+      // One loop over the tile's slots -- probe (n = -1), steps, fold slot (n = tot), flush (n = tot + 1: nothing is
+      // published, the last d_x0 is consumed) -- so that the gather, the staging and the scatter exist ONCE in the
+      // instruction stream (the kernel is instruction-cache bound otherwise: profiles/ncu_r2c_bwd.md).
+#pragma unroll 1
+      for (int n = -1; n <= tot + 1; ++n) {
+        const bool probe = n < 0, virt = n == tot, flush = n > tot;
+        if (virt && !any_empty) continue;
+        int flag = 1;
+        float occ = 1.f;
+        float x0[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) x0[c] = 0.f;
+        Pos cur = {0.f, 0.f, 0.f, 0.f};
+        if (!probe && !virt && !flush) {
+          const Sched sc = lp_sched(n, M);
+          float depth, delta;
+          lp_depth_delta(sc, me.near, me.far, depth, delta);
+          cur.x = me.ox + depth * me.dx; cur.y = me.oy + depth * me.dy; cur.z = me.oz + depth * me.dz;
+          if (M.contract) lp_contract(cur.x, cur.y, cur.z);
+          cur.oob = M.mask_oob ? lp_in_bounds(cur.x, cur.y, cur.z) : 1.f;
+          if (SCAF) occ = lp_nearest(SC, me.b, cur.x, cur.y, cur.z);
+          if (SCAF && !lp_bar_any(3 + grp, GT, occ != 0.f)) {
+            flag = 2;  // nobody's sample is occupied: the slot changes nothing
+          } else {
+            const bool hit = lp_gather_regs<C>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
+            flag = lp_bar_any(3 + grp, GT, hit) ? 1 : 0;
+            any_empty |= flag == 0;
+          }
+        }
+        const bool tile_slot = flag == 1 && !probe && !flush;  // this slot ends with a dW GEMM (and produces a d_x0)
+        if (!flush) {
+          // ---- publish the slot: operand row (full slots) into tensor memory, flag + occupancy into shared memory ----
+          if (n_slot > 0) lp_mbar_wait(x0_free, (n_slot - 1) & 1);
+          if (flag == 1) {
+            lp_tc_fence_after();
+            lp_stage_row<C, 16>(tme + ST_X, x0);
+            lp_tmem_wait_st();
+            lp_tc_fence_before();
+          }
+          if (SCAF) occs[s] = occ;  // (single buffer: the decoder thread reads it before it releases x0_free)
+          if (s == 0) flags[n_slot & 1] = flag;
+          lp_mbar_arrive(x0_full);
+          ++n_slot;
+        }
+        if (pend && (tile_slot || flush)) {
+          // ---- consume the pending d_x0: read it, clear its accumulator columns, release them, scatter ----
+          float dxp[C];
+          lp_mbar_wait(dx_full, n_dx & 1);
+          ++n_dx;
+          lp_tc_fence_after();
+          lp_tmem_ld<C>(tme + ST_D + 32, dxp);
+          lp_tmem_zero<C>(tme + ST_D + 32);
+          lp_tmem_wait_st();
+          lp_tc_fence_before();
+          lp_mbar_arrive(dx_free);
+          if (pend_scatter) {  // (warp-uniform) quad-transposed, footprint-merging reduction into the grid gradient
+#pragma unroll
+            for (int c = 0; c < C; ++c) dxp[c] *= prev.oob;
+            lp_splat_quad<C>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, me.active && prev.oob != 0.f, dxp);
+          }
+          pend = false;
+        }
+        if (tile_slot) {  // the slot's x0 rows go into the dW tile once the previous GEMM is done
+          if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
+          ++n_dw;
+          lp_tile_row<C>(gs + W::STK, W::CH_X0, s, x0);
+          lp_fence_async_smem();
+          lp_mbar_arrive(xt_full);
+          pend = true;
+          pend_scatter = !virt;  // the fold slot's d_x0 is discarded (zero features touch no texel)
+          prev = cur;
+        }
+      }
+      ++n_dw;  // the tile's tail: encoding product
+    }
+#else
     LP_SETMAXNREG_DEC(LP_WS_REGS_MEM);
     int n_slot = 0, n_dw = 0, n_dx = 0;  // slots staged; dW GEMMs the decoder group has issued; d_x0 rows consumed
     for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
@@ -300,6 +395,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
       }
       ++n_dw;  // the tile's tail: encoding product
     }
+#endif
   } else {
     // =================================================================================================================
     // decoder group
@@ -355,6 +451,149 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
       float e_raw = 0.f, e_lg0 = 0.f, e_lg1 = 0.f, e_lg2 = 0.f, G_raw = 0.f, L0 = 0.f, L1 = 0.f, L2 = 0.f;
       bool any_empty = false;
 
+#if LP_MLP_COMPACT
+#pragma unroll 1
+      for (int step = -1; step <= tot; ++step) {
+        const bool probe = step < 0, virt = step == tot;
+        if (virt && !any_empty) break;
+        // ---- the slot's operand, flag and occupancy from the memory group ----
+        lp_mbar_wait(x0_full, n_slot & 1);
+        const int flag = flags[n_slot & 1];
+        const float occ = SCAF ? occs[s] : 1.f;
+        ++n_slot;
+        if (flag == 2) {  // unoccupied slot (scaffold): nothing happens
+          lp_mbar_arrive(x0_free);
+          continue;
+        }
+        float raw = e_raw, lg0 = e_lg0, lg1 = e_lg1, lg2 = e_lg2;  // flag 0: every sample is empty -> the probe's decoder output
+        if (flag == 1) {
+          // ------------------------------ forward recompute ------------------------------
+          if (leader) {
+            lp_tc_fence_after();
+            LP_ISSUE(ST_X, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, 16, wi);
+            lp_tc_commit(bar0);
+          }
+          LP_TCG_WAIT(bar0, phase0);
+          lp_mbar_arrive(x0_free);  // the operand columns (and the slot's flag) may be overwritten
+          if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);  // the previous dW GEMM has consumed the tiles (long done)
+          // the two trunk layers: one body (bias + ReLU + dW tile + hi/lo operand + next product), executed twice
+#pragma unroll 1
+          for (int l = 0; l < 2; ++l) {
+            lp_tmem_ld<32>(tme + ST_D, v);
+            lp_tmem_zero<32>(tme + ST_D);
+            const float* bl = F + I::FB + 32 * l;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bl[j], 0.f);
+            lp_tile_row<32>(gs + W::STK, l == 0 ? W::CH_H1 : W::CH_TR, s, v);
+            lp_stage_row<32, 32>(tme + ST_A, v);
+            // l == 1: opacity | colour hidden; the product overwrites D columns 32.., where the previous slot's d_x0 may still sit
+            LP_TC_HANDOFF(if (l == 1 && n_dx > 0) lp_mbar_wait(dx_free, (n_dx - 1) & 1);
+                          LP_ISSUE(ST_A, l == 0 ? w_t1h : w_och, l == 0 ? w_t1l : w_ocl, 2, 0, l == 0 ? 512 : 1024, l == 0 ? 32 : 64, 32, wi);
+                          lp_tc_commit(bar));
+            LP_TC_WAIT();
+          }
+          {  // output layer (4 wide) on the CUDA cores, exact fp32; two partial sums per output shorten the FMA chains
+            float r0 = F[I::FBL + 3], r1 = 0.f;
+            lp_tmem_ld<32>(tme + ST_D, v);
+            lp_tmem_zero<32>(tme + ST_D);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              v[j] = fmaxf(v[j] + F[I::FB + 64 + j], 0.f);
+              v[j + 1] = fmaxf(v[j + 1] + F[I::FB + 64 + j + 1], 0.f);
+              r0 = fmaf(v[j], F[I::FWO + j], r0);
+              r1 = fmaf(v[j + 1], F[I::FWO + j + 1], r1);
+            }
+            raw = r0 + r1;
+            lp_tile_row<32>(gs + W::STK, W::CH_HO, s, v);
+            float a0 = F[I::FBL], a1 = F[I::FBL + 1], a2 = F[I::FBL + 2], b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            lp_tmem_ld<32>(tme + ST_D + 32, v);
+            lp_tmem_zero<32>(tme + ST_D + 32);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 eb = ecb[k * GT];  // enc x Wc0 + b (stands in for the bias)
+              v[4 * k] = fmaxf(v[4 * k] + eb.x, 0.f); v[4 * k + 1] = fmaxf(v[4 * k + 1] + eb.y, 0.f);
+              v[4 * k + 2] = fmaxf(v[4 * k + 2] + eb.z, 0.f); v[4 * k + 3] = fmaxf(v[4 * k + 3] + eb.w, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float4 w0 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
+              const float4 w1 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j + 4);
+              a0 = fmaf(v[j], w0.x, a0); a1 = fmaf(v[j], w0.y, a1); a2 = fmaf(v[j], w0.z, a2);
+              b0 = fmaf(v[j + 1], w1.x, b0); b1 = fmaf(v[j + 1], w1.y, b1); b2 = fmaf(v[j + 1], w1.z, b2);
+            }
+            lg0 = a0 + b0; lg1 = a1 + b1; lg2 = a2 + b2;
+            lp_tile_row<32>(gs + W::STK, W::CH_HC, s, v);
+          }
+          if (probe) {  // decoder output at zero features, for the compositing of the empty steps
+            e_raw = raw; e_lg0 = lg0; e_lg1 = lg1; e_lg2 = lg2;
+            // the next slot's first product is issued without a hand-off: everybody must be done with the accumulators
+            lp_tmem_wait_st();
+            lp_tc_fence_before();
+            lp_bar_sync(1 + grp, GT);
+            continue;
+          }
+        }
+        // ------------------------------ compositing gradient (one call site for full and empty slots) ------------------------------
+        float g_raw = G_raw, dl0 = L0, dl1 = L1, dl2 = L2;  // fold slot: the summed gradients of the tile's empty steps
+        if (!virt) {
+          const Sched sc = lp_sched(step, M);
+          float depth, delta;
+          lp_depth_delta(sc, near, far, depth, delta);
+          cb.grad(M, ray, step, step == tot - 1, raw, lg0, lg1, lg2, depth, delta, occ, g_raw, dl0, dl1, dl2);
+        }
+        if (flag == 0) {  // every sample of the group is empty: gradients summed for the fold slot
+          G_raw += g_raw; L0 += dl0; L1 += dl1; L2 += dl2;
+          any_empty = true;
+          lp_mbar_arrive(x0_free);
+          continue;
+        }
+        lp_tile8(gs + W::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
+        // ------------------------------ backward sweep ------------------------------
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = g_raw * F[I::FWO + j];  // d_ho
+        lp_gate_row<32>(v, gs + W::STK, W::CH_HO, s);
+        lp_tile_row<32>(gs + W::DY, 4, s, v);
+#if LP_BWD_XT_TF32
+        lp_stage_row_tf32<32>(tme + ST_A, v);
+#else
+        lp_stage_row<32, 32>(tme + ST_A, v);        // [d_ho | d_hc]: packed hi words at columns 0..31, lo at 32..63
+#endif
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {                                     // d_hc
+          const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
+          v[j] = fmaf(dl0, w.x, fmaf(dl1, w.y, dl2 * w.z));
+        }
+        lp_gate_row<32>(v, gs + W::STK, W::CH_HC, s);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) S[j] += v[j];
+        lp_tile_row<32>(gs + W::DY, 8, s, v);
+#if LP_BWD_XT_TF32
+        lp_stage_row_tf32<32>(tme + ST_A + 32, v);
+        LP_TC_ROUND(LP_ISSUE_TF32(ST_D, ST_A, w_xt, 8, 0, 2048, 32); lp_tc_commit(bar));
+#else
+        lp_stage_row<32, 32>(tme + ST_A + 16, v);
+        LP_TC_ROUND(LP_ISSUE(ST_A, w_xt, w_xtl, 4, 0, 1024, 32, 32, wi); lp_tc_commit(bar));
+#endif
+        // d_t and d_h1: one body (gate + dW tile + hi/lo operand + next product), executed twice; the second product (d_x0,
+        // for the memory group) and the dW GEMM that rides on its hand-off are not waited for
+#pragma unroll 1
+        for (int l = 0; l < 2; ++l) {
+          lp_tmem_ld<32>(tme + ST_D, v);
+          lp_tmem_zero<32>(tme + ST_D);
+          lp_gate_row<32>(v, gs + W::STK, l == 0 ? W::CH_TR : W::CH_H1, s);
+          lp_tile_row<32>(gs + W::DY, l == 0 ? 0 : 12, s, v);
+          lp_stage_row<32, 32>(tme + ST_A, v);
+          if (l == 0) {
+            LP_TC_ROUND(LP_ISSUE(ST_A, w_xhh, w_xhl, 2, 0, 512, 32, 32, wi); lp_tc_commit(bar));
+          } else {
+            lp_fence_async_smem();  // this step's tile writes -> visible to the tensor core
+            LP_TC_HANDOFF(LP_ISSUE_D(ST_D + 32, ST_A, w_x0h, w_x0l, 2, 0, 512, C, 32, wi); lp_tc_commit(dx_full);
+                          lp_mbar_wait(xt_full, n_xt & 1); LP_ABL_DW(lp_ws_issue_dw_part<C>(tmem, gs, wi)); lp_tc_commit(bar_dw));
+          }
+        }
+        ++n_dw; ++n_dx; ++n_xt;
+      }
+#else
       for (int step = -1; step <= tot; ++step) {
         const bool probe = step < 0, virt = step == tot;
         if (virt && !any_empty) break;
@@ -493,6 +732,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
                       lp_mbar_wait(xt_full, n_xt & 1); LP_ABL_DW(lp_ws_issue_dw_part<C>(tmem, gs, wi)); lp_tc_commit(bar_dw));
         ++n_dw; ++n_dx; ++n_xt;
       }
+#endif
       // ---- per-tile tail: encoding gradient = S Wc0^T, and the encoding's share of dWc0 = enc^T S ----
       if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);
       {

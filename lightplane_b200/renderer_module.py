@@ -329,8 +329,8 @@ class LightplaneRenderer(torch.nn.Module):
     ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Decoder outputs at 3-D points (renderer_module.py:183-253): `opacity [n_rays, n_pts]` = gain * softplus(raw)
         and `features [n_rays, n_pts, chn]` = sigmoid(colour logits), both times the scaffold's occupancy; `chn` is the
-        width of the colour layer in the parameter layout (zero-padded to 16: padded channels read sigmoid(0) = 0.5, as
-        in the reference).  Evaluated THROUGH the ray-march kernels on degenerate rays (see `eval_opacity_at_points`):
+        width of the colour layer in the parameter layout (zero-padded to 16 at initialisation: those channels read
+        sigmoid(0) = 0.5, as in the reference).  Evaluated THROUGH the ray-march kernels on degenerate rays (see `eval_opacity_at_points`):
         the opacity from a two-sample march; the colours from a one-sample march with a saturating gain (render weight
         1 - exp(-gain * softplus(raw)) == 1 in fp32), which makes the rendered feature the decoder's colour."""
         n_rays = pts.shape[0]
@@ -348,17 +348,11 @@ class LightplaneRenderer(torch.nn.Module):
                       color_grid=color_feature_grid)
         _, nlt, _ = lightplane_renderer(rays, feature_grid, self.get_decoder_params(), num_samples=2,
                                         gain=if_not_none_else(gain, self.gain), **common)
-        _, _, col = lightplane_renderer(rays, feature_grid, self.get_decoder_params(), num_samples=1, gain=3.0e38, **common)
-        opacity = (0.5 * nlt).reshape(shape)
+        # every channel of the colour layer as laid out in `mlp_params` (the padded ones too: whatever their weights hold)
         chn = int(self.n_hidden_color[-1])
-        if chn > col.shape[1]:  # the layout's padded colour channels: zero weights and biases -> sigmoid(0), times the occupancy
-            pad = col.new_full((col.shape[0], chn - col.shape[1]), 0.5)
-            if scaffold is not None:
-                p = rays.origins
-                if contract:
-                    p = _contract_points(p)
-                pad = pad * _nearest_occupancy(scaffold, p, rays.grid_idx.long())[:, None]
-            col = torch.cat([col, pad], dim=1)
+        all_chn = DecoderParams(self.mlp_params, *self._n_hidden, chn)
+        _, _, col = lightplane_renderer(rays, feature_grid, all_chn, num_samples=1, gain=3.0e38, **common)
+        opacity = (0.5 * nlt).reshape(shape)
         return opacity, col.reshape(*shape, chn)
 
     @torch.no_grad()
@@ -438,22 +432,3 @@ def _check_renderer_ray_encoding_input(
         " set ray_embedding_num_harmonics=None."
     )
 
-
-def _contract_points(p: torch.Tensor) -> torch.Tensor:
-    """MERF contraction then x0.5 (ray_util.py:12-45), for the host-side occupancy lookup of `eval_decoder_at_points`."""
-    a = p.abs()
-    n = a.max(dim=-1, keepdim=True).values
-    scaled = p / n.clamp_min(1e-12)
-    out = torch.where(n > 1, torch.where((a - n).abs() <= 1e-8, (2 - 1 / a.clamp_min(1e-12)) * (p / a.clamp_min(1e-12)), scaled), p)
-    return 0.5 * out
-
-
-def _nearest_occupancy(scaffold: torch.Tensor, p: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-    """Nearest-cell value of a `[B,D,H,W]` scaffold at points `p [P,3]` (x->W, y->H, z->D, align_corners=False), zero
-    outside the grid and outside [-1,1]^3 (grid_sample_util.py:717-777)."""
-    B, D, H, W = scaffold.shape
-    size = p.new_tensor([W, H, D])
-    i = torch.round(((p + 1) * 0.5) * size - 0.5)  # ties to even, as F.grid_sample(mode="nearest")
-    ok = ((i >= 0) & (i < size)).all(-1) & (p.abs() <= 1).all(-1)
-    i = i.clamp_min(0).minimum(size - 1).long()
-    return scaffold[idx, i[:, 2], i[:, 1], i[:, 0]] * ok.to(scaffold.dtype)
