@@ -285,9 +285,9 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-in-volume", action="store_true", help="skip the second timed workload (all samples inside the volume)")
-    ap.add_argument("--tile-walk", dest="tile_walk", action="store_true",
-                    help="pass the image width (ray_image_width): rays are walked as 16x8-pixel tiles instead of 128-ray "
-                         "scan-line runs (measured slower with per-thread reductions: profiles/bench_r2_ablation.md)")
+    ap.add_argument("--no-tile-walk", dest="tile_walk", action="store_false",
+                    help="do not pass the image width (ray_image_width): the kernels then walk 128-ray scan-line runs instead "
+                         "of 16x8-pixel tiles (measured: profiles/bench_r2_ablation.md)")
     ap.add_argument("--per-rank-cameras", action="store_true",
                     help="N>1: a different camera per rank (default: the same view on every rank, so that the scaling "
                          "number measures the machine and not the spread of per-view work)")

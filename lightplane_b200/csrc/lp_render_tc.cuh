@@ -331,8 +331,8 @@ LP_DEVICE void lp_stage_row(unsigned taddr_a, const float (&x)[N]) {
   lp_tmem_st<N / 2>(taddr_a + LO, lo);
 }
 
-// per-group tensor-memory columns (forward): A hi 0..15 / lo 16..31, encoding hi 32..47 / lo 48..63, D 64..127
-constexpr int TC_A = 0, TC_E = 32, TC_D = 64, TC_GROUP_COLS = 128;
+// per-group tensor-memory columns (forward): A hi 0..15 / lo 16..31, D 32..95
+constexpr int TC_A = 0, TC_D = 32, TC_GROUP_COLS = 96;  // (up to five groups fit the SM's 512 columns)
 
 // single-issuer form (LP_TC_ISSUERS == 1 builds): D(n columns) = A(K) x W, three bf16 products per 16-wide k-step
 LP_DEVICE void lp_issue_layer(unsigned tbase, int d_col, int a_col, lp_kdesc_t whi, lp_kdesc_t wlo, int ksteps, int k0,

@@ -331,8 +331,9 @@ class LightplaneRenderer(torch.nn.Module):
         and `features [n_rays, n_pts, chn]` = sigmoid(colour logits), both times the scaffold's occupancy; `chn` is the
         width of the colour layer in the parameter layout (zero-padded to 16 at initialisation: those channels read
         sigmoid(0) = 0.5, as in the reference).  Evaluated THROUGH the ray-march kernels on degenerate rays (see `eval_opacity_at_points`):
-        the opacity from a two-sample march; the colours from a one-sample march with a saturating gain (render weight
-        1 - exp(-gain * softplus(raw)) == 1 in fp32), which makes the rendered feature the decoder's colour."""
+        the opacity from a two-sample march; the colours from a one-sample march with a saturating gain of 1e30 (render weight
+        1 - exp(-gain * softplus(raw)) == 1 in fp32 for raw > -60, and gain * softplus stays finite, so an unoccupied
+        scaffold cell still multiplies it to an exact 0), which makes the rendered feature the decoder's colour."""
         n_rays = pts.shape[0]
         assert pts.ndim == 3 and pts.shape[2] == 3 and tuple(pts_to_grid_idx.shape) == (n_rays,)
         if rays_encoding is not None:
@@ -351,7 +352,7 @@ class LightplaneRenderer(torch.nn.Module):
         # every channel of the colour layer as laid out in `mlp_params` (the padded ones too: whatever their weights hold)
         chn = int(self.n_hidden_color[-1])
         all_chn = DecoderParams(self.mlp_params, *self._n_hidden, chn)
-        _, _, col = lightplane_renderer(rays, feature_grid, all_chn, num_samples=1, gain=3.0e38, **common)
+        _, _, col = lightplane_renderer(rays, feature_grid, all_chn, num_samples=1, gain=1.0e30, **common)
         opacity = (0.5 * nlt).reshape(shape)
         return opacity, col.reshape(*shape, chn)
 
