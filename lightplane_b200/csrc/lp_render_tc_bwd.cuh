@@ -450,7 +450,6 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
       for (int j = 0; j < 32; ++j) S[j] = 0.f;
       float e_raw = 0.f, e_lg0 = 0.f, e_lg1 = 0.f, e_lg2 = 0.f, G_raw = 0.f, L0 = 0.f, L1 = 0.f, L2 = 0.f;
       bool any_empty = false;
-      bool pre_t0 = false;  // the previous slot's last hand-off already issued this slot's first product (if the slot is full)
 
 #if LP_MLP_COMPACT
 #pragma unroll 1
@@ -467,11 +466,9 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           continue;
         }
         float raw = e_raw, lg0 = e_lg0, lg1 = e_lg1, lg2 = e_lg2;  // flag 0: every sample is empty -> the probe's decoder output
-        const bool t0_issued = pre_t0;
-        pre_t0 = false;
         if (flag == 1) {
           // ------------------------------ forward recompute ------------------------------
-          if (leader && !t0_issued) {
+          if (leader) {
             lp_tc_fence_after();
             LP_ISSUE(ST_X, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, 16, wi);
             lp_tc_commit(bar0);
@@ -590,21 +587,8 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
             LP_TC_ROUND(LP_ISSUE(ST_A, w_xhh, w_xhl, 2, 0, 512, 32, 32, wi); lp_tc_commit(bar));
           } else {
             lp_fence_async_smem();  // this step's tile writes -> visible to the tensor core
-            // The NEXT slot's first product rides on this hand-off too, ahead of the dW GEMM in the (in-order) tensor
-            // pipe: its operand was staged by the memory group a whole step ago and its accumulator columns were
-            // cleared above, so the next slot starts with its result (almost) there instead of queueing behind the GEMM.
-            const bool has_next = step < tot - 1 || (step == tot - 1 && any_empty);
             LP_TC_HANDOFF(LP_ISSUE_D(ST_D + 32, ST_A, w_x0h, w_x0l, 2, 0, 512, C, 32, wi); lp_tc_commit(dx_full);
-                          if (has_next) {
-                            lp_mbar_wait(x0_full, n_slot & 1);
-                            if (flags[n_slot & 1] == 1) {
-                              lp_tc_fence_after();
-                              LP_ISSUE(ST_X, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, 16, wi);
-                              lp_tc_commit(bar0);
-                            }
-                          }
                           lp_mbar_wait(xt_full, n_xt & 1); LP_ABL_DW(lp_ws_issue_dw_part<C>(tmem, gs, wi)); lp_tc_commit(bar_dw));
-            pre_t0 = has_next;
           }
         }
         ++n_dw; ++n_dx; ++n_xt;
