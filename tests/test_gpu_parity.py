@@ -114,6 +114,7 @@ def test_renderer_layer_counts_tensor_core_path(lib, layers, C, n, scaf):
         # "max norm is noisy: ReLU-gate flips").  Measured 1-2e-3 on these random decoders with 6-8 hidden layers (the host
         # emulation gives the same figure, i.e. arithmetic, not a race); 2/2/2 stays at 2e-5..2e-4.
         tol = TOL_GMLP_TINY if k == "g_mlp" else (3e-3 if k.startswith("g_") else TOL)
+        print(f"layers {layers} C {C}: {k} {rel_err(v, want[k]):.2e}")
         assert rel_err(v, want[k]) < tol, (layers, k, rel_err(v, want[k]))
 
 

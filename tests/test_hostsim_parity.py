@@ -149,3 +149,15 @@ def test_hostsim_single_sample_with_background_samples(lib, hidden):
     for k, v in got.items():
         tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
         assert rel_err(v, want[k]) < tol, (hidden, k, rel_err(v, want[k]))
+
+
+def test_hostsim_renderer_several_tiles_per_group(lib):
+    """More ray tiles than groups (the emulated device has 2 SMs x 2 groups): every group walks several tiles in
+    sequence -- the tile tail, the next tile's per-ray constant and probe slot, and the memory group running ahead
+    across the tile boundary in the warp-specialised backward."""
+    c = coherent_case(load_case("render_triplane_inf_gain"), n=1100, pixel=0.004, mask_oob=0)
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cpu", ray_image_width=0)
+    for k, v in got.items():
+        tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
+        assert rel_err(v, want[k]) < tol, (k, rel_err(v, want[k]))

@@ -172,6 +172,14 @@ def main():
         try:
             r = run_impl(ref, ref.DecoderParams, dp, grids, rays_t, enc, cot, loss_kind, **kw)
             row["reference_ok"] = True
+            if n <= 4096:  # the reference's OWN two fp32 paths against each other: the agreement any fp32 implementation can have
+                import types
+                naive = types.SimpleNamespace(Rays=ref.Rays, lightplane_renderer=ref.lightplane_renderer_naive)
+                rn = run_impl(naive, ref.DecoderParams, dp, grids, rays_t, enc, cot, loss_kind, **kw)
+                row["reference_naive_vs_triton"] = {k: rel(rn[k], r[k]) for k in r}
+                if not args.skip_ours:
+                    o_ = run_impl(lp, lp.DecoderParams, dp, grids, rays_t, enc, cot, loss_kind, **kw)
+                    row["ours_vs_reference_naive"] = {k: rel(o_[k], rn[k]) for k in r}
             if not args.skip_ours:
                 o = run_impl(lp, lp.DecoderParams, dp, grids, rays_t, enc, cot, loss_kind, **kw)
                 row["mean_rel"] = {k: rel(o[k], r[k]) for k in r}
