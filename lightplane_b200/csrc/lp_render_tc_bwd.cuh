@@ -157,10 +157,13 @@ LP_DEVICE void lp_ws_issue_encw_part(unsigned tmem, unsigned char* gs, int wi) {
 #ifndef LP_MEM_SINGLE_LOOP
 #define LP_MEM_SINGLE_LOOP 0
 #endif
-#ifndef LP_WS_REGS_MLP
-#define LP_WS_REGS_MLP 168
-#define LP_WS_REGS_MEM 88
+// Register split between the roles (setmaxnreg; the two values add up to 256 = 64 K registers / 256 threads per role).
+// C = 16: 168 / 88 (splits down to 152 / 104 measure the same); C = 32: the memory threads hold two 32-float rows and spill at
+// 88 registers -- 128 / 128 (no re-allocation at all) makes the cfg5 backward 140.0 -> 118.4 ms (152/104: 132.4, 136/120: 120.3).
+#ifndef LP_WS_REGS_MEM
+#define LP_WS_REGS_MEM(C) ((C) == 16 ? 88 : 128)
 #endif
+#define LP_WS_REGS_MLP(C) (256 - LP_WS_REGS_MEM(C))
 
 template <int C, bool SCAF>
 __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMarch M, LpDecoder D, LpGridSet G, LpGridSet SC,
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
     // memory group
     // =================================================================================================================
 #if LP_MEM_SINGLE_LOOP
-    LP_SETMAXNREG_DEC(LP_WS_REGS_MEM);
+    if constexpr (LP_WS_REGS_MEM(C) < 128) LP_SETMAXNREG_DEC(LP_WS_REGS_MEM(C));
     int n_slot = 0, n_dw = 0, n_dx = 0;  // slots staged; dW GEMMs the decoder group has issued; d_x0 rows consumed
     for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
       const Ray1 me = lp_load_ray1(R, lp_tile_ray(M, tile, s), G.g[0].B);
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
       ++n_dw;  // the tile's tail: encoding product
     }
 #else
-    LP_SETMAXNREG_DEC(LP_WS_REGS_MEM);
+    if constexpr (LP_WS_REGS_MEM(C) < 128) LP_SETMAXNREG_DEC(LP_WS_REGS_MEM(C));
     int n_slot = 0, n_dw = 0, n_dx = 0;  // slots staged; dW GEMMs the decoder group has issued; d_x0 rows consumed
     for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
       const Ray1 me = lp_load_ray1(R, lp_tile_ray(M, tile, s), G.g[0].B);
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
     // =================================================================================================================
     // decoder group
     // =================================================================================================================
-    LP_SETMAXNREG_INC(LP_WS_REGS_MLP);
+    if constexpr (LP_WS_REGS_MLP(C) > 128) LP_SETMAXNREG_INC(LP_WS_REGS_MLP(C));
     const bool leader = lane == 0;  // lane 0 of each of the group's four warps issues its share of every product
     const int wi = wig;
     const float* F = reinterpret_cast<const float*>(sm + I::F32);
