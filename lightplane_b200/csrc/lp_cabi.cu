@@ -343,6 +343,14 @@ static int lp_splat_geometry(int C, int* lpr, int* vpl) {
   return LP_OK;
 }
 
+// the plain splat kernels address grid rows with 32-bit indices
+static int lp_splat_rows_fit(const LpGridSet& G, const char* name) {
+  const LpGrid& g = G.g[G.n - 1];
+  const long long rows = g.base / G.C + (long long)g.B * g.D * g.H * g.W;
+  if (rows > 0x7fffffffLL) LP_FAIL(LP_ERR_UNSUPPORTED, "%s: %lld grid rows; the splatter supports < 2^31", name, rows);
+  return LP_OK;
+}
+
 int lp_splat_forward(void* stream, const lp_march_cfg* cfg, const lp_rays* rays, const float* valid_mask,
                      const lp_grid_list* out, float* weight_grid) {
   LpRays R; LpMarch M; LpGridSet O;
@@ -353,6 +361,7 @@ int lp_splat_forward(void* stream, const lp_march_cfg* cfg, const lp_rays* rays,
   if ((rc = lp_make_rays(rays, &R, O.C))) return rc;
   if (R.n == 0) return LP_OK;
   if ((rc = lp_splat_geometry(O.C, &lpr, &vpl))) return rc;
+  if ((rc = lp_splat_rows_fit(O, "out"))) return rc;
   const int threads = 128, rays_per_block = threads / lpr;
   dim3 g((R.n + rays_per_block - 1) / rays_per_block), b(threads);
   cudaStream_t st = (cudaStream_t)stream;
@@ -375,6 +384,7 @@ int lp_splat_backward(void* stream, const lp_march_cfg* cfg, const lp_rays* rays
   if ((rc = lp_make_rays(rays, &R, GG.C))) return rc;
   if (R.n == 0) return LP_OK;
   if ((rc = lp_splat_geometry(GG.C, &lpr, &vpl))) return rc;
+  if ((rc = lp_splat_rows_fit(GG, "grad_grid"))) return rc;
   const int threads = 128, rays_per_block = threads / lpr;
   dim3 g((R.n + rays_per_block - 1) / rays_per_block), b(threads);
   cudaStream_t st = (cudaStream_t)stream;

@@ -2,7 +2,8 @@
 //
 // Plain splatter (no MLP): HBM/L2-atomic bound byte work.  A sub-warp of `lpr` lanes owns one ray
 // and each lane a float4 chunk of the channels, so every tap of every sample is one coalesced
-// `red.global.add.v4.f32` row segment (forward) or one 16-byte gather per lane (backward); feature
+// `red.global.add.v4.f32` row segment (forward) or one 16-byte gather per lane (backward); the lanes
+// of the sub-warp share the march (one lane per sample works out the taps, shuffles hand them round); feature
 // and weight grid are accumulated in ONE march (the reference launches its kernel twice,
 // lightplane_splatter.py:505,539).  Semantics: splatter_fw.py:71-165, splatter_bw.py:75-180.
 //
@@ -12,44 +13,132 @@
 
 #include "lp_render_generic.cuh"
 
+// Taps of one grid as 32-bit ROW indices into the flat [rows, C] tensor (the host checks rows < 2^31) and weights;
+// same corner order and zero-padding rule as lp_taps.  Returns the tap count (8 voxel / 4 plane) and whether any
+// tap has a non-zero weight.
+LP_DEVICE int lp_taps_rows(const LpGrid& g, int row_base, int b, float x, float y, float z, int* row, float* w,
+                           bool& any) {
+  any = false;
+  if (g.kind == LP_VOXEL) {
+    float x0, fx, y0, fy, z0, fz;
+    lp_axis(x, g.W, x0, fx);
+    lp_axis(y, g.H, y0, fy);
+    lp_axis(z, g.D, z0, fz);
+    const int bb = row_base + b * g.D * g.H * g.W;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float wx, wy, wz;
+      int ix, iy, iz;
+      lp_corner(x0, fx, c & 1, g.W, wx, ix);
+      lp_corner(y0, fy, (c >> 1) & 1, g.H, wy, iy);
+      lp_corner(z0, fz, (c >> 2) & 1, g.D, wz, iz);
+      w[c] = wx * wy * wz;
+      any |= w[c] != 0.f;
+      row[c] = bb + (iz * g.H + iy) * g.W + ix;
+    }
+    return 8;
+  }
+  float u, v;
+  int U, V;
+  if (g.kind == LP_PLANE_XY) { u = x; v = y; U = g.W; V = g.H; }
+  else if (g.kind == LP_PLANE_XZ) { u = x; v = z; U = g.W; V = g.D; }
+  else { u = y; v = z; U = g.H; V = g.D; }
+  float u0, fu, v0, fv;
+  lp_axis(u, U, u0, fu);
+  lp_axis(v, V, v0, fv);
+  const int bb = row_base + b * U * V;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float wu, wv;
+    int iu, iv;
+    lp_corner(u0, fu, c & 1, U, wu, iu);
+    lp_corner(v0, fv, (c >> 1) & 1, V, wv, iv);
+    w[c] = wu * wv;
+    any |= w[c] != 0.f;
+    row[c] = bb + iv * U + iu;
+  }
+#pragma unroll
+  for (int c = 4; c < 8; ++c) { w[c] = 0.f; row[c] = 0; }
+  return 4;
+}
+
+// The march of one ray is shared by the `lpr` lanes of its sub-warp: in every round lane j works out the position and
+// the taps of step (round * lpr + j) -- the index arithmetic is done once per sample, not once per lane -- a ballot
+// names the steps of the round that touch the grid at all, and for each of those the owning lane's row indices and
+// weights are broadcast by shuffles while every lane reduces (forward) or gathers (backward) its own float4 channel
+// chunks of the row.  Steps outside the grid (most of a scene view's samples) cost nothing beyond their share of the
+// tap arithmetic.
+struct LpSplatLane {
+  int sub, base;      // lane within the sub-warp, first lane of the sub-warp
+  unsigned mask;      // the sub-warp's lanes
+  long long ray;
+  float ox, oy, oz, dx, dy, dz, near, far, vm;
+  int b;
+};
+LP_DEVICE bool lp_splat_lane(const LpRays& R, const LpGridSet& G, const float* valid, int lpr, LpSplatLane& L) {
+  const int lane = threadIdx.x & 31;
+  L.sub = lane % lpr;
+  L.base = lane - L.sub;
+  L.mask = lpr >= 32 ? 0xffffffffu : (((1u << lpr) - 1u) << L.base);
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  L.ray = warp_global * (LP_WARP / lpr) + lane / lpr;
+  if (L.ray >= R.n) return false;  // whole sub-warps leave together; no block-level barriers below
+  const long long ray = L.ray;
+  L.vm = valid ? valid[ray] : 1.f;
+  L.ox = R.org[3 * ray]; L.oy = R.org[3 * ray + 1]; L.oz = R.org[3 * ray + 2];
+  L.dx = R.dir[3 * ray]; L.dy = R.dir[3 * ray + 1]; L.dz = R.dir[3 * ray + 2];
+  L.near = R.near[ray]; L.far = R.far[ray];
+  L.b = min(max(R.gidx[ray], 0), G.g[0].B - 1);
+  return true;
+}
+// position of this lane's step of the round; false when the step does not exist or is masked out
+LP_DEVICE bool lp_splat_point(const LpSplatLane& L, const LpMarch& M, int step, float& x, float& y, float& z) {
+  const int tot = M.S + M.S_inf;
+  const float depth = lp_depth(min(step, tot - 1), L.near, L.far, M.S, M.S_inf, M.disparity_at_inf);
+  x = L.ox + depth * L.dx; y = L.oy + depth * L.dy; z = L.oz + depth * L.dz;
+  if (M.contract) lp_contract(x, y, z);
+  return step < tot && !(M.mask_oob && lp_in_bounds(x, y, z) == 0.f);
+}
+
 template <int VPL>
 __global__ void lp_splat_fwd_kernel(LpRays R, LpMarch M, LpGridSet OUT, float* __restrict__ weight,
                                     const float* __restrict__ valid, int lpr) {
-  const int lane = threadIdx.x & 31;
-  const int sub = lane % lpr, rays_per_warp = LP_WARP / lpr;
-  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long ray = warp_global * rays_per_warp + lane / lpr;
-  if (ray >= R.n) return;  // no block-level barriers below
+  LpSplatLane L;
+  if (!lp_splat_lane(R, OUT, valid, lpr, L)) return;
   const int C = OUT.C;
-  const float vm = valid ? valid[ray] : 1.f;
   float4 f[VPL];
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
-    f[v] = lp_ldg4(R.enc + ray * C + 4 * (sub + lpr * v));
-    f[v].x *= vm; f[v].y *= vm; f[v].z *= vm; f[v].w *= vm;
+    f[v] = lp_ldg4(R.enc + L.ray * C + 4 * (L.sub + lpr * v));
+    f[v].x *= L.vm; f[v].y *= L.vm; f[v].z *= L.vm; f[v].w *= L.vm;
   }
-  const float ox = R.org[3 * ray], oy = R.org[3 * ray + 1], oz = R.org[3 * ray + 2];
-  const float dx = R.dir[3 * ray], dy = R.dir[3 * ray + 1], dz = R.dir[3 * ray + 2];
-  const float near = R.near[ray], far = R.far[ray];
-  const int b = min(max(R.gidx[ray], 0), OUT.g[0].B - 1);
+  const bool splat_weight = L.sub == 0 && weight != nullptr && L.vm != 0.f;
   const int tot = M.S + M.S_inf;
-  for (int step = 0; step < tot; ++step) {
-    const float depth = lp_depth(step, near, far, M.S, M.S_inf, M.disparity_at_inf);
-    float x = ox + depth * dx, y = oy + depth * dy, z = oz + depth * dz;
-    if (M.contract) lp_contract(x, y, z);
-    if (M.mask_oob && lp_in_bounds(x, y, z) == 0.f) continue;
+  for (int step0 = 0; step0 < tot; step0 += lpr) {
+    float x, y, z;
+    const bool live = lp_splat_point(L, M, step0 + L.sub, x, y, z);
     for (int gi = 0; gi < OUT.n; ++gi) {
-      long long off[8];
+      int row[8];
       float w[8];
-      const int nt = lp_taps(OUT.g[gi], C, b, x, y, z, off, w);
+      bool any;
+      const int nt = lp_taps_rows(OUT.g[gi], (int)(OUT.g[gi].base / C), L.b, x, y, z, row, w, any);
+      unsigned todo = (__ballot_sync(L.mask, live && any) & L.mask) >> L.base;
+      while (todo) {
+        const int j = __ffs((int)todo) - 1;
+        todo &= todo - 1;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        if (t < nt && w[t] != 0.f) {
+        for (int t = 0; t < 8; ++t) {
+          if (t < nt) {
+            const float wt = __shfl_sync(L.mask, w[t], j, lpr);
+            const int rt = __shfl_sync(L.mask, row[t], j, lpr);
+            if (wt != 0.f) {
+              float* dst = OUT.data + (long long)rt * C + 4 * L.sub;
 #pragma unroll
-          for (int v = 0; v < VPL; ++v)
-            lp_red_add4(OUT.data + off[t] + 4 * (sub + lpr * v), w[t] * f[v].x, w[t] * f[v].y,
-                        w[t] * f[v].z, w[t] * f[v].w);
-          if (sub == 0 && weight != nullptr && vm != 0.f) lp_red_add1(weight + off[t] / C, w[t] * vm);
+              for (int v = 0; v < VPL; ++v)
+                lp_red_add4(dst + 4 * lpr * v, wt * f[v].x, wt * f[v].y, wt * f[v].z, wt * f[v].w);
+              if (splat_weight) lp_red_add1(weight + rt, wt * L.vm);
+            }
+          }
         }
       }
     }
@@ -59,38 +148,39 @@ __global__ void lp_splat_fwd_kernel(LpRays R, LpMarch M, LpGridSet OUT, float* _
 template <int VPL>
 __global__ void lp_splat_bwd_kernel(LpRays R, LpMarch M, LpGridSet GG, const float* __restrict__ valid,
                                     float* __restrict__ g_feat, int lpr) {
-  const int lane = threadIdx.x & 31;
-  const int sub = lane % lpr, rays_per_warp = LP_WARP / lpr;
-  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long ray = warp_global * rays_per_warp + lane / lpr;
-  if (ray >= R.n) return;
+  LpSplatLane L;
+  if (!lp_splat_lane(R, GG, valid, lpr, L)) return;
   const int C = GG.C;
-  const float vm = valid ? valid[ray] : 1.f;
   float4 acc[VPL];
 #pragma unroll
   for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float ox = R.org[3 * ray], oy = R.org[3 * ray + 1], oz = R.org[3 * ray + 2];
-  const float dx = R.dir[3 * ray], dy = R.dir[3 * ray + 1], dz = R.dir[3 * ray + 2];
-  const float near = R.near[ray], far = R.far[ray];
-  const int b = min(max(R.gidx[ray], 0), GG.g[0].B - 1);
   const int tot = M.S + M.S_inf;
-  for (int step = 0; step < tot; ++step) {
-    const float depth = lp_depth(step, near, far, M.S, M.S_inf, M.disparity_at_inf);
-    float x = ox + depth * dx, y = oy + depth * dy, z = oz + depth * dz;
-    if (M.contract) lp_contract(x, y, z);
-    if (M.mask_oob && lp_in_bounds(x, y, z) == 0.f) continue;
+  for (int step0 = 0; step0 < tot; step0 += lpr) {
+    float x, y, z;
+    const bool live = lp_splat_point(L, M, step0 + L.sub, x, y, z);
     for (int gi = 0; gi < GG.n; ++gi) {
-      long long off[8];
+      int row[8];
       float w[8];
-      const int nt = lp_taps(GG.g[gi], C, b, x, y, z, off, w);
+      bool any;
+      const int nt = lp_taps_rows(GG.g[gi], (int)(GG.g[gi].base / C), L.b, x, y, z, row, w, any);
+      unsigned todo = (__ballot_sync(L.mask, live && any) & L.mask) >> L.base;
+      while (todo) {
+        const int j = __ffs((int)todo) - 1;
+        todo &= todo - 1;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        if (t < nt && w[t] != 0.f) {
+        for (int t = 0; t < 8; ++t) {
+          if (t < nt) {
+            const float wt = __shfl_sync(L.mask, w[t], j, lpr);
+            const int rt = __shfl_sync(L.mask, row[t], j, lpr);
+            if (wt != 0.f) {
+              const float* src = GG.data + (long long)rt * C + 4 * L.sub;
 #pragma unroll
-          for (int v = 0; v < VPL; ++v) {
-            const float4 g = lp_ldg4(GG.data + off[t] + 4 * (sub + lpr * v));
-            acc[v].x = fmaf(w[t], g.x, acc[v].x); acc[v].y = fmaf(w[t], g.y, acc[v].y);
-            acc[v].z = fmaf(w[t], g.z, acc[v].z); acc[v].w = fmaf(w[t], g.w, acc[v].w);
+              for (int v = 0; v < VPL; ++v) {
+                const float4 g = lp_ldg4(src + 4 * lpr * v);
+                acc[v].x = fmaf(wt, g.x, acc[v].x); acc[v].y = fmaf(wt, g.y, acc[v].y);
+                acc[v].z = fmaf(wt, g.z, acc[v].z); acc[v].w = fmaf(wt, g.w, acc[v].w);
+              }
+            }
           }
         }
       }
@@ -98,8 +188,8 @@ __global__ void lp_splat_bwd_kernel(LpRays R, LpMarch M, LpGridSet GG, const flo
   }
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
-    float* o = g_feat + ray * C + 4 * (sub + lpr * v);
-    o[0] = acc[v].x * vm; o[1] = acc[v].y * vm; o[2] = acc[v].z * vm; o[3] = acc[v].w * vm;
+    float* o = g_feat + L.ray * C + 4 * (L.sub + lpr * v);
+    o[0] = acc[v].x * L.vm; o[1] = acc[v].y * L.vm; o[2] = acc[v].z * L.vm; o[3] = acc[v].w * L.vm;
   }
 }
 

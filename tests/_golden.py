@@ -112,6 +112,14 @@ def oracle_splat_case(c, dtype=torch.float64):
     return {k: v.detach() for k, v in res.items()}
 
 
+def plain_splat_case(n=70, channels=32, **kw):
+    """A plain (no MLP) splatter case: `synthetic_splat_case` without its MLP entries."""
+    c = synthetic_splat_case(n=n, c_in=channels, c_out=channels, **kw)
+    for k in ("mlp_params", "n_hidden", "input_grid", "input_sizes"):
+        c.pop(k)
+    return c
+
+
 def coherent_case(c, n=64, pixel=0.02, seed=5, batch_blocks=True, mask_oob=None, plane=None, scaffold_res=None,
                   origin=(0.1, -0.15, -2.2), near=1.0, far=3.4):
     """A copy of golden case `c` whose rays are replaced by `n` neighbouring pixels of a pinhole camera

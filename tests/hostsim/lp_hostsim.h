@@ -57,6 +57,7 @@ struct WarpCtx {
   std::barrier<>* bar;
   uint32_t slots_u[32];
   int pred[32];
+  std::atomic<unsigned> gcnt[32] = {};  // rendezvous counters of sub-warp groups (keyed by the group's lowest lane)
 };
 
 struct BlockCtx {
@@ -138,22 +139,36 @@ inline unsigned char* dyn_smem() { return g_ctx->block->smem; }
 static inline void __syncthreads() { lp_hostsim::g_ctx->block->bar->arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { lp_hostsim::g_ctx->warp->bar->arrive_and_wait(); }
 
+// Rendezvous of the lanes named by `mask` (a strict subset of the warp: sub-warp shuffles / ballots
+// executed while other sub-warps of the same warp are elsewhere).  Every group of one warp keeps
+// the same mask for the whole kernel, so a monotonic counter per lowest lane is a reusable barrier.
+static inline void lp_hs_group_sync(unsigned mask) {
+  auto* w = lp_hostsim::g_ctx->warp;
+  if (mask == 0xffffffffu) { w->bar->arrive_and_wait(); return; }
+  const unsigned n = (unsigned)__builtin_popcount(mask);
+  std::atomic<unsigned>& c = w->gcnt[__builtin_ctz(mask)];
+  const unsigned target = (c.fetch_add(1, std::memory_order_acq_rel) / n + 1) * n;
+  while (c.load(std::memory_order_acquire) < target) std::this_thread::yield();
+}
 template <class T>
-static inline T lp_hs_exchange(T v, int src_lane) {
+static inline T lp_hs_exchange(T v, int src_lane, unsigned mask = 0xffffffffu) {
   static_assert(sizeof(T) == 4, "32-bit shuffles only");
   auto* w = lp_hostsim::g_ctx->warp;
   uint32_t bits;
   std::memcpy(&bits, &v, 4);
   w->slots_u[lp_hostsim::g_ctx->lane] = bits;
-  w->bar->arrive_and_wait();
+  lp_hs_group_sync(mask);
   uint32_t got = w->slots_u[src_lane & 31];
-  w->bar->arrive_and_wait();
+  lp_hs_group_sync(mask);
   T out;
   std::memcpy(&out, &got, 4);
   return out;
 }
 template <class T>
-static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return lp_hs_exchange(v, src); }
+static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
+  const int lane = lp_hostsim::g_ctx->lane;
+  return lp_hs_exchange(v, (lane & ~(width - 1)) | (src & (width - 1)), mask);
+}
 template <class T>
 static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) {
   return lp_hs_exchange(v, lp_hostsim::g_ctx->lane ^ m);
@@ -163,13 +178,14 @@ static inline T __shfl_down_sync(unsigned, T v, int d, int = 32) {
   int l = lp_hostsim::g_ctx->lane + d;
   return lp_hs_exchange(v, l > 31 ? lp_hostsim::g_ctx->lane : l);
 }
-static inline unsigned __ballot_sync(unsigned, int pred) {
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
   auto* w = lp_hostsim::g_ctx->warp;
   w->pred[lp_hostsim::g_ctx->lane] = pred ? 1 : 0;
-  w->bar->arrive_and_wait();
+  lp_hs_group_sync(mask);
   unsigned m = 0;
-  for (int i = 0; i < 32; ++i) m |= (w->pred[i] ? 1u : 0u) << i;
-  w->bar->arrive_and_wait();
+  for (int i = 0; i < 32; ++i)
+    if ((mask >> i) & 1u) m |= (w->pred[i] ? 1u : 0u) << i;
+  lp_hs_group_sync(mask);
   return m;
 }
 static inline int __reduce_min_sync(unsigned, int v) {

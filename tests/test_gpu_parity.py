@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from _golden import (case_names, coherent_case, load_case, synthetic_case, oracle_render_case, oracle_splat_case, rel_err,
-                     renderer_cfg, splat_cfg)
+                     plain_splat_case, renderer_cfg, splat_cfg)
 from _lowlevel import render_case, splat_case
 
 pytestmark = pytest.mark.gpu
@@ -332,3 +332,16 @@ def test_no_cpu_fallback():
                    near=torch.zeros(n), far=torch.ones(n), encoding=torch.zeros(n, 32))
     with pytest.raises(RuntimeError):
         lp.lightplane_renderer(rays, [torch.zeros(1, 4, 4, 4, 16)], dp, num_samples=4, gain=1.0)
+
+
+@pytest.mark.parametrize("channels,samples,triplane,mask", [(4, 5, False, 1), (8, 7, True, 0), (32, 13, False, 1), (64, 9, True, 1),
+                                                            (128, 6, False, 0), (256, 40, True, 1)])
+def test_gpu_plain_splatter_shared_march(lib, channels, samples, triplane, mask):
+    """Sub-warps of 1..32 lanes per ray (lp_splat.cuh: one lane per sample works out the taps, shuffles hand them round),
+    sample counts that are not multiples of the sub-warp width, a ray count that leaves sub-warps of the last warp idle."""
+    c = plain_splat_case(n=70, channels=channels, samples=samples, samples_inf=3, triplane=triplane, mask_oob=mask, batch=2)
+    want = oracle_splat_case(c)
+    got = splat_case(lib, c, "cuda")
+    for k, v in got.items():
+        assert torch.isfinite(v).all(), k
+        assert rel_err(v, want[k]) < 2e-4, (k, rel_err(v, want[k]))

@@ -7,8 +7,8 @@ import subprocess
 import pytest
 import torch
 
-from _golden import (case_names, coherent_case, load_case, oracle_render_case, oracle_splat_case, rel_err, synthetic_case,
-                     synthetic_splat_case)
+from _golden import (case_names, coherent_case, load_case, oracle_render_case, oracle_splat_case, rel_err, plain_splat_case,
+                     synthetic_case, synthetic_splat_case)
 from _lowlevel import render_case, splat_case
 from lightplane_b200 import _cabi
 
@@ -161,3 +161,16 @@ def test_hostsim_renderer_several_tiles_per_group(lib):
     for k, v in got.items():
         tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
         assert rel_err(v, want[k]) < tol, (k, rel_err(v, want[k]))
+
+
+@pytest.mark.parametrize("channels,samples,triplane,mask", [(4, 5, False, 1), (8, 7, True, 0), (32, 13, False, 1), (64, 9, True, 1),
+                                                            (128, 6, False, 0), (256, 40, True, 1)])
+def test_hostsim_plain_splatter_shared_march(lib, channels, samples, triplane, mask):
+    """Sub-warps of 1..32 lanes per ray (lp_splat.cuh: one lane per sample works out the taps, shuffles hand them round),
+    sample counts that are not multiples of the sub-warp width, a ray count that leaves sub-warps of the last warp idle."""
+    c = plain_splat_case(n=70, channels=channels, samples=samples, samples_inf=3, triplane=triplane, mask_oob=mask, batch=2)
+    want = oracle_splat_case(c)
+    got = splat_case(lib, c, "cpu")
+    for k, v in got.items():
+        assert torch.isfinite(v).all(), k
+        assert rel_err(v, want[k]) < 2e-4, (k, rel_err(v, want[k]))
