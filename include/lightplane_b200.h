@@ -176,6 +176,36 @@ int lp_splat_normalize(void* stream, float* feature_grid, float* weight_grid, in
 int lp_int_to_randn(void* stream, const int32_t* x1, const int32_t* x2, int32_t seed,
                     float* out, int64_t n);
 
+/* ---- glue of the reference's renderer MODULE, fused (optional: the ops above do not need them) ----
+ *
+ * Ray encoding  encoding[r, :] = weight @ embed(normalize(directions[r])) + bias  with the harmonic
+ * embedding  [sin(2^k d) | sin(2^k d + pi/2) | d]  (k < n_harmonics; per phase: x, y, z blocks of
+ * n_harmonics columns).  Replaces, in one launch, `F.normalize` + `calc_harmonic_embedding`
+ * (ray_utils.py:181-212) + `harmonic_ray_embedding_linear` (renderer_module.py:578-601).
+ * weight fp32 [encoding_dim, 3 + 6 * n_harmonics] row-major (torch.nn.Linear layout), bias fp32
+ * [encoding_dim] or NULL, encoding fp32 [num_rays, encoding_dim] fully written, 16-byte aligned. */
+int lp_ray_embed_forward(void* stream, int64_t num_rays, const float* directions, int32_t n_harmonics,
+                         const float* weight, const float* bias, int32_t encoding_dim, float* encoding);
+
+/* Its backward: grad_weight [encoding_dim, 3 + 6 * n_harmonics] and grad_bias [encoding_dim] (may be
+ * NULL) ACCUMULATE the sums over rays (caller zero-fills); directions get no gradient. */
+int lp_ray_embed_backward(void* stream, int64_t num_rays, const float* directions, int32_t n_harmonics,
+                          const float* grad_encoding, int32_t encoding_dim, float* grad_weight,
+                          float* grad_bias);
+
+/* Background epilogue of the module (renderer_module.py:552-563):
+ *   T = exp(-nlt);  out = features + T * bg_color;  alpha = return_log_transmittance ? -nlt : 1 - T.
+ * nlt, alpha fp32 [num_rays]; features, out fp32 [num_rays, channels]; bg_color fp32 [channels]. */
+int lp_bg_composite_forward(void* stream, int64_t num_rays, int32_t channels, const float* nlt,
+                            const float* features, const float* bg_color,
+                            int32_t return_log_transmittance, float* alpha, float* out);
+
+/* Its backward: grad_nlt [num_rays] fully written from grad_alpha [num_rays] and grad_out
+ * [num_rays, channels] (either may be NULL = zero); d features = grad_out (no kernel needed). */
+int lp_bg_composite_backward(void* stream, int64_t num_rays, int32_t channels, const float* nlt,
+                             const float* bg_color, int32_t return_log_transmittance,
+                             const float* grad_alpha, const float* grad_out, float* grad_nlt);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,10 @@ _PROTOTYPES = {
     "lp_mlp_splat_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lp_splat_normalize": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32]),
     "lp_int_to_randn": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int64]),
+    "lp_ray_embed_forward": (C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, _P, C.c_int32, _P]),
+    "lp_ray_embed_backward": (C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, C.c_int32, _P, _P]),
+    "lp_bg_composite_forward": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32, _P, _P]),
+    "lp_bg_composite_backward": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

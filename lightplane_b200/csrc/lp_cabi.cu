@@ -8,6 +8,7 @@
 #include "lp_common.cuh"
 #include "lp_render_generic.cuh"
 #include "lp_splat.cuh"
+#include "lp_ray_embed.cuh"
 #include "lp_render_tc.cuh"
 #include "lp_render_tc_bwd.cuh"
 #include "lp_render_tc_cg.cuh"
@@ -417,6 +418,78 @@ int lp_int_to_randn(void* stream, const int32_t* x1, const int32_t* x2, int32_t 
   LP_LAUNCH(lp_int_to_randn_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x1, x2,
             (int)seed, out, (long long)n);
   return lp_check_launch("lp_int_to_randn");
+}
+
+// ---- module glue: ray encoding and background epilogue (lp_ray_embed.cuh) ------------------------
+static int lp_embed_check(int64_t n, const float* directions, int32_t n_harmonics, int32_t out_dim, int* items) {
+  if (n < 0) LP_FAIL(LP_ERR_INVALID_ARG, "num_rays < 0");
+  if (n > 0 && !directions) LP_FAIL(LP_ERR_INVALID_ARG, "directions is NULL");
+  if (n_harmonics < 0 || n_harmonics > LP_EMB_MAX_HARM)
+    LP_FAIL(LP_ERR_UNSUPPORTED, "n_harmonics=%d not in [0,%d]", n_harmonics, LP_EMB_MAX_HARM);
+  if (out_dim < 4 || out_dim % 4 != 0) LP_FAIL(LP_ERR_UNSUPPORTED, "encoding_dim (%d) must be a positive multiple of 4", out_dim);
+  *items = (3 + 6 * n_harmonics + 1) * (out_dim / 4);
+  if (*items > LP_EMB_MAX_ITEMS * LP_EMB_TILE)
+    LP_FAIL(LP_ERR_UNSUPPORTED, "(3 + 6 * n_harmonics + 1) * encoding_dim / 4 = %d exceeds %d", *items, LP_EMB_MAX_ITEMS * LP_EMB_TILE);
+  return LP_OK;
+}
+
+int lp_ray_embed_forward(void* stream, int64_t num_rays, const float* directions, int32_t n_harmonics,
+                         const float* weight, const float* bias, int32_t encoding_dim, float* encoding) {
+  int rc, items;
+  if ((rc = lp_embed_check(num_rays, directions, n_harmonics, encoding_dim, &items))) return rc;
+  if (num_rays == 0) return LP_OK;
+  if (!weight || !encoding) LP_FAIL(LP_ERR_INVALID_ARG, "weight / encoding is NULL");
+  if (((uintptr_t)encoding & 15) != 0) LP_FAIL(LP_ERR_INVALID_ARG, "encoding is not 16-byte aligned");
+  const int in_dim = 3 + 6 * n_harmonics;
+  const size_t bytes = sizeof(float) * ((size_t)encoding_dim * in_dim + encoding_dim + (size_t)LP_EMB_TILE * (in_dim + 1));
+  if (LP_SET_SMEM(lp_ray_embed_fwd_kernel, bytes)) LP_FAIL(LP_ERR_CUDA, "cannot raise dynamic smem limit");
+  long long blocks = (num_rays + LP_EMB_TILE - 1) / LP_EMB_TILE;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  LP_LAUNCH(lp_ray_embed_fwd_kernel, dim3((unsigned)blocks), dim3(LP_EMB_TILE), bytes, (cudaStream_t)stream, directions,
+            (long long)num_rays, (int)n_harmonics, weight, bias, (int)encoding_dim, encoding);
+  return lp_check_launch("lp_ray_embed_forward");
+}
+
+int lp_ray_embed_backward(void* stream, int64_t num_rays, const float* directions, int32_t n_harmonics,
+                          const float* grad_encoding, int32_t encoding_dim, float* grad_weight, float* grad_bias) {
+  int rc, items;
+  if ((rc = lp_embed_check(num_rays, directions, n_harmonics, encoding_dim, &items))) return rc;
+  if (num_rays == 0) return LP_OK;
+  if (!grad_encoding || !grad_weight) LP_FAIL(LP_ERR_INVALID_ARG, "grad_encoding / grad_weight is NULL");
+  if (((uintptr_t)grad_encoding & 15) != 0) LP_FAIL(LP_ERR_INVALID_ARG, "grad_encoding is not 16-byte aligned");
+  const int in_dim = 3 + 6 * n_harmonics;
+  const size_t bytes = sizeof(float) * (size_t)LP_EMB_TILE * ((in_dim + 2) + (encoding_dim + 4));
+  if (LP_SET_SMEM(lp_ray_embed_bwd_kernel, bytes)) LP_FAIL(LP_ERR_CUDA, "cannot raise dynamic smem limit");
+  long long blocks = (num_rays + LP_EMB_TILE - 1) / LP_EMB_TILE;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  LP_LAUNCH(lp_ray_embed_bwd_kernel, dim3((unsigned)blocks), dim3(LP_EMB_TILE), bytes, (cudaStream_t)stream, directions,
+            (long long)num_rays, (int)n_harmonics, grad_encoding, (int)encoding_dim, grad_weight, grad_bias);
+  return lp_check_launch("lp_ray_embed_backward");
+}
+
+int lp_bg_composite_forward(void* stream, int64_t num_rays, int32_t channels, const float* nlt, const float* features,
+                            const float* bg_color, int32_t return_log_transmittance, float* alpha, float* out) {
+  if (num_rays < 0 || channels < 1) LP_FAIL(LP_ERR_INVALID_ARG, "num_rays < 0 or channels < 1");
+  if (num_rays == 0) return LP_OK;
+  if (!nlt || !features || !bg_color || !alpha || !out) LP_FAIL(LP_ERR_INVALID_ARG, "NULL pointer");
+  long long blocks = (num_rays + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  LP_LAUNCH(lp_bg_fwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (long long)num_rays,
+            (int)channels, nlt, features, bg_color, (int)return_log_transmittance, alpha, out);
+  return lp_check_launch("lp_bg_composite_forward");
+}
+
+int lp_bg_composite_backward(void* stream, int64_t num_rays, int32_t channels, const float* nlt, const float* bg_color,
+                             int32_t return_log_transmittance, const float* grad_alpha, const float* grad_out,
+                             float* grad_nlt) {
+  if (num_rays < 0 || channels < 1) LP_FAIL(LP_ERR_INVALID_ARG, "num_rays < 0 or channels < 1");
+  if (num_rays == 0) return LP_OK;
+  if (!nlt || !bg_color || !grad_nlt) LP_FAIL(LP_ERR_INVALID_ARG, "NULL pointer");
+  long long blocks = (num_rays + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  LP_LAUNCH(lp_bg_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (long long)num_rays,
+            (int)channels, nlt, bg_color, (int)return_log_transmittance, grad_alpha, grad_out, grad_nlt);
+  return lp_check_launch("lp_bg_composite_backward");
 }
 
 // ---- MLP splatter -----------------------------------------------------------------------------

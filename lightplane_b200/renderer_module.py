@@ -17,6 +17,7 @@ import torch
 
 from .lightplane_renderer import lightplane_renderer
 from .misc_utils import if_not_none_else, process_and_flatten_grid
+from .module_ops import bg_composite, ray_embedding_linear, ray_embedding_supported
 from .mlp_utils import DecoderParams, flattened_decoder_params_to_list, init_decoder_params
 from .ray_utils import Rays, calc_harmonic_embedding, calc_harmonic_embedding_dim, jitter_near_far
 
@@ -228,9 +229,12 @@ class LightplaneRenderer(torch.nn.Module):
             color_grid_sizes=color_grid_sizes,
             ray_image_width=ray_image_width,
         )
-        transmittance = torch.exp(-nlt)
-        features = features + transmittance[..., None] * bg
-        alpha = -nlt if return_log_t else 1.0 - transmittance
+        if features.is_cuda and not bg.requires_grad:
+            alpha, features = bg_composite(nlt, features, bg, return_log_t)  # one launch each way (csrc/lp_ray_embed.cuh)
+        else:
+            transmittance = torch.exp(-nlt)
+            features = features + transmittance[..., None] * bg
+            alpha = -nlt if return_log_t else 1.0 - transmittance
         return ray_length, alpha, features
 
     # ------------------------------------------------------------------------------------
@@ -246,6 +250,11 @@ class LightplaneRenderer(torch.nn.Module):
         if not self.enable_direction_dependent_colors:
             return ray_directions.new_zeros(ray_directions.shape[0], self.rays_encoding_dim)
         assert self.ray_embedding_num_harmonics is not None
+        lin = self.harmonic_ray_embedding_linear
+        if (ray_directions.is_cuda and not ray_directions.requires_grad and ray_directions.dim() == 2
+                and ray_embedding_supported(self.ray_embedding_num_harmonics, lin.out_features)):
+            # fused normalize + embedding + Linear, forward and backward (csrc/lp_ray_embed.cuh)
+            return ray_embedding_linear(ray_directions, lin.weight, lin.bias, self.ray_embedding_num_harmonics)
         unit = torch.nn.functional.normalize(ray_directions, dim=-1)
         return self.harmonic_ray_embedding_linear(
             calc_harmonic_embedding(unit, self.ray_embedding_num_harmonics)
