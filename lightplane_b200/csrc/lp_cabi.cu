@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cstdlib>
 #include "lp_common.cuh"
 #include "lp_render_generic.cuh"
 #include "lp_splat.cuh"
@@ -199,6 +200,14 @@ int lp_abi_version(void) { return LP_ABI_VERSION; }
 const char* lp_last_error(void) { return g_err; }
 int lp_is_device_build(void) { return LP_IS_DEVICE_BUILD; }
 
+// LP_ONLY_GENERIC=1 in the environment routes every renderer launch to the generic fp32 kernels (lp_render_generic.cuh):
+// a measurement aid -- it gives the error of a plain fp32 implementation of the same decoder against the fp64 oracle, the
+// floor the tensor-core paths' tolerances are judged against (tests/test_gpu_parity.py).
+static bool lp_only_generic() {
+  const char* e = getenv("LP_ONLY_GENERIC");
+  return e != nullptr && e[0] == '1';
+}
+
 static int lp_render_common(const lp_march_cfg* cfg, const lp_decoder_spec* spec, const lp_rays* rays,
                             const lp_grid_list* grid, const lp_grid_list* color_grid,
                             const lp_grid_list* scaffold, const float* mlp_params, LpRenderArgs* a) {
@@ -241,26 +250,27 @@ int lp_render_forward(void* stream, const lp_march_cfg* cfg, const lp_decoder_sp
     LP_FAIL(LP_ERR_INVALID_ARG, "an output pointer is NULL");
   if (features_stride < a.D.n_feat) LP_FAIL(LP_ERR_INVALID_ARG, "features_stride < num_color_used");
   cudaStream_t st = (cudaStream_t)stream;
-  if (lptc::lp_tc_render_supported(a)) {
+  const bool fast = !lp_only_generic();
+  if (fast && lptc::lp_tc_render_supported(a)) {
     if ((rc = lptc::lp_tc_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance, out_features,
                                          features_stride)))
       LP_FAIL(rc, "fast forward launch setup failed");
     return lp_check_launch("lp_render_forward(fast)");
   }
-  if (lptc::lp_cg_render_supported(a)) {
+  if (fast && lptc::lp_cg_render_supported(a)) {
     if ((rc = lptc::lp_cg_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance, out_features,
                                          features_stride)))
       LP_FAIL(rc, "colour-grid forward launch setup failed");
     return lp_check_launch("lp_render_forward(colour grid)");
   }
-  if (lptc::lp_tcw_forward_supported(a)) {
+  if (fast && lptc::lp_tcw_forward_supported(a)) {
     if ((rc = lptc::lp_tcw_render_forward(st, a, mlp_params, out_ray_length, out_neg_log_transmittance, out_features,
                                           features_stride)))
       LP_FAIL(rc, "hidden-64 forward launch setup failed");
     return lp_check_launch("lp_render_forward(hidden 64)");
   }
   lptc::DeepPlan dpl;
-  if (lptc::lp_deep_plan(a, &dpl)) {
+  if (fast && lptc::lp_deep_plan(a, &dpl)) {
     if ((rc = lptc::lp_deep_render_forward(st, a, dpl, mlp_params, out_ray_length, out_neg_log_transmittance, out_features,
                                            features_stride)))
       LP_FAIL(rc, "layer-count-general forward launch setup failed");
@@ -302,20 +312,21 @@ int lp_render_backward(void* stream, const lp_march_cfg* cfg, const lp_decoder_s
   io.g_len = grad_ray_length; io.g_nlt = grad_neg_log_transmittance; io.g_feat = grad_features;
   io.g_feat_stride = grad_features_stride;
   io.g_grid = grad_grid; io.g_cgrid = grad_color_grid; io.g_params = grad_mlp_params; io.g_enc = grad_encoding;
-  if (lptc::lp_tc_render_supported(a)) {
+  const bool fast = !lp_only_generic();
+  if (fast && lptc::lp_tc_render_supported(a)) {
     if ((rc = lptc::lp_tc_render_backward(st, a, mlp_params, io))) LP_FAIL(rc, "fast backward launch setup failed");
     return lp_check_launch("lp_render_backward(fast)");
   }
-  if (lptc::lp_cg_render_supported(a)) {
+  if (fast && lptc::lp_cg_render_supported(a)) {
     if ((rc = lptc::lp_cg_render_backward(st, a, mlp_params, io))) LP_FAIL(rc, "colour-grid backward launch setup failed");
     return lp_check_launch("lp_render_backward(colour grid)");
   }
-  if (lptc::lp_tcw_forward_supported(a)) {
+  if (fast && lptc::lp_tcw_forward_supported(a)) {
     if ((rc = lptc::lp_tcw_render_backward(st, a, mlp_params, io))) LP_FAIL(rc, "hidden-64 backward launch setup failed");
     return lp_check_launch("lp_render_backward(hidden 64)");
   }
   lptc::DeepPlan dpl;
-  if (lptc::lp_deep_plan(a, &dpl)) {
+  if (fast && lptc::lp_deep_plan(a, &dpl)) {
     if ((rc = lptc::lp_deep_render_backward(st, a, dpl, mlp_params, io))) LP_FAIL(rc, "layer-count-general backward launch setup failed");
     return lp_check_launch("lp_render_backward(deep)");
   }

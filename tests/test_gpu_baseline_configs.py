@@ -38,6 +38,16 @@ def _bench_problem(side, seed, dev):
 @pytest.mark.parametrize("loss_kind,tile_walk", [("randsign", False), ("mse", False), ("randsign", True)])
 def test_renderer_bench_camera_4096x128_vs_oracle(loss_kind, tile_walk):
     """configs[1]/[2] workload shape (bench camera, 128 samples, 64^2x16 triplane, 2/2/2 h32) on 64x64 rays."""
+    errs = bench_camera_errors(loss_kind, tile_walk)
+    print(f"bench-camera 4096x128 [{loss_kind}, tile_walk={tile_walk}] errors vs fp64 oracle:", {k: f"{v:.1e}" for k, v in errs.items()})
+    for k in ("ray_length", "nlt", "features"):
+        assert errs[k] < TOL_OUT, errs
+    assert errs["g_grid"] < TOL_GRAD and errs["g_enc"] < TOL_GRAD, errs
+    assert errs["g_mlp"] < TOL_GMLP, errs
+
+
+def bench_camera_errors(loss_kind, tile_walk):
+    """Relative errors of every output and gradient against the fp64 oracle (also used by tools/fp32_floor.py)."""
     import lightplane_b200 as lp
     from oracle import lightplane_oracle as O
 
@@ -72,11 +82,7 @@ def test_renderer_bench_camera_4096x128_vs_oracle(loss_kind, tile_walk):
     errs["g_grid"] = rel_err(torch.cat([x.reshape(-1, C) for x in grads[:3]], 0), ograds[0])
     errs["g_mlp"] = rel_err(grads[3], ograds[1])
     errs["g_enc"] = rel_err(grads[4], ograds[2])
-    print(f"bench-camera 4096x128 [{loss_kind}, tile_walk={tile_walk}] errors vs fp64 oracle:", {k: f"{v:.1e}" for k, v in errs.items()})
-    for k in ("ray_length", "nlt", "features"):
-        assert errs[k] < TOL_OUT, errs
-    assert errs["g_grid"] < TOL_GRAD and errs["g_enc"] < TOL_GRAD, errs
-    assert errs["g_mlp"] < TOL_GMLP, errs
+    return errs
 
 
 def test_splatter_cfg4_shape_8192x256_vs_oracle():

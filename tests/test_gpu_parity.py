@@ -112,7 +112,8 @@ def test_renderer_layer_counts_tensor_core_path(lib, layers, C, n, scaf):
         # deeper decoders: more ReLU gates whose pre-activation (accurate to ~1e-5 of the summed terms with the bf16 hi+lo
         # products) lies within rounding of zero; a flipped gate is an O(1) error of that sample's gradient (SURVEY 8d:
         # "max norm is noisy: ReLU-gate flips").  Measured 1-2e-3 on these random decoders with 6-8 hidden layers (the host
-        # emulation gives the same figure, i.e. arithmetic, not a race); 2/2/2 stays at 2e-5..2e-4.
+        # emulation gives the same figure, i.e. arithmetic, not a race); 2/2/2 stays at 2e-5..4e-4.  profiles/fp32_floor_r2.md has the
+        # same problems through the generic fp32 kernels (3e-6..2e-4) and the gate-flip arithmetic.
         tol = TOL_GMLP_TINY if k == "g_mlp" else (3e-3 if k.startswith("g_") else TOL)
         print(f"layers {layers} C {C}: {k} {rel_err(v, want[k]):.2e}")
         assert rel_err(v, want[k]) < tol, (layers, k, rel_err(v, want[k]))
