@@ -329,7 +329,10 @@ def main():
     model = lp.LightplaneRenderer(num_samples=S, color_chn=COLOR, grid_chn=C, mlp_hidden_chn=H,
                                   opacity_init_bias=-1.0).to(dev)
     shapes = [[1, 1, PLANE, PLANE, C], [1, PLANE, 1, PLANE, C], [1, PLANE, PLANE, 1, C]]
-    grids = [(0.5 * torch.randn(s, device=dev)).requires_grad_(True) for s in shapes]
+    # the three planes live in ONE flat [rows, C] parameter + a host size table (the reference API's flat form,
+    # misc_utils.py:201-234): no per-call concatenation, one tensor to all-reduce
+    grid_rows = sum(s[0] * s[1] * s[2] * s[3] for s in shapes)
+    grids = [(0.5 * torch.randn(grid_rows, C, device=dev)).requires_grad_(True)]
     params = grids + list(model.parameters())
     cam_seed = 1000 + (rank if args.per_rank_cameras else 0)
     hint = args.width if args.tile_walk else None
@@ -353,7 +356,7 @@ def main():
         for p in params:
             p.grad = None
         rays = lp.Rays(directions=rays_t[0], origins=rays_t[1], grid_idx=rays_t[2], near=rays_t[3], far=rays_t[4])
-        _, _, feat = model(rays, grids, ray_image_width=hint)
+        _, _, feat = model(rays, grids[0], grid_sizes=shapes, ray_image_width=hint)
         loss = ((feat - tgt) ** 2).mean()
         if cfg5:  # configs[4]: the Splatter runs on the same sharded rays; its accumulators are all-reduced inside the op
             srays = lp.Rays(directions=rays_t[0], origins=rays_t[1], grid_idx=rays_t[2], near=rays_t[3], far=rays_t[4],
