@@ -151,6 +151,13 @@ LP_DEVICE void lp_mbar_wait(unsigned long long* bar, int parity) {
         : "memory");
   }
 }
+// One lane of the (converged) warp: `elect.sync`.  Unlike `lane == 0` the compiler knows that exactly one thread passes,
+// so single-thread instructions behind it (tcgen05.mma, tcgen05.commit) are emitted without an election loop.
+LP_DEVICE bool lp_elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 // plain arrival of one thread (release semantics at CTA scope)
 LP_DEVICE void lp_mbar_arrive(unsigned long long* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(lp_smem_u32(bar)) : "memory");
@@ -315,3 +322,5 @@ LP_DEVICE bool lp_bar_any(int id, int nthreads, bool pred) {
 }
 #endif  // !LP_HOSTSIM
 
+// Broadcast of lane 0's value: tells the compiler the value is warp-uniform (it may then live in uniform registers).
+#define LP_WARP_UNIFORM(x) __shfl_sync(0xffffffffu, (x), 0)

@@ -408,7 +408,10 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
   using I = Img<C>;
   LP_DYN_SMEM(unsigned char, sm);
   const int tid = threadIdx.x;
-  const int grp = tid / GT, ngroups = blockDim.x / GT, wig = (tid >> 5) & 3;  // warp in group = TMEM lane quarter
+  // warp index via a broadcast shuffle: what derives from it (group, tensor-/shared-memory operand addresses, mbarrier)
+  // is then known to be warp-uniform and stays on the uniform datapath (see lp_render_tc_bwd.cuh)
+  const int warp_u = LP_WARP_UNIFORM(tid >> 5);
+  const int grp = warp_u >> 2, ngroups = blockDim.x / GT, wig = warp_u & 3;  // warp in group = TMEM lane quarter
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + I::FWD_END);  // one per group
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
   lp_build_img<C>(sm, params, D);
@@ -421,9 +424,10 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
   lp_tc_fence_before();
   __syncthreads();
   lp_tc_fence_after();
-  const unsigned tbase = *tmem_slot + (unsigned)(grp * TC_GROUP_COLS);
+  const unsigned tbase = LP_WARP_UNIFORM(*tmem_slot) + (unsigned)(grp * TC_GROUP_COLS);
   const unsigned tme = lp_taddr(tbase, wig, 0);  // this thread's lane, column 0 of the group
-  const bool leader = (tid & 31) == 0;  // lane 0 of each of the group's four warps issues k-step `wig` (lp_issue_layer_part)
+  // one elected lane (elect.sync: the compiler then emits the tcgen05 issue without an election loop) of each of the
+  // group's four warps issues k-step `wig` (lp_issue_layer_part)
   lp_tmem_zero<32>(tme + TC_D);
   lp_tmem_zero<32>(tme + TC_D + 32);
   const float* F = reinterpret_cast<const float*>(sm + I::F32);
@@ -449,7 +453,7 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
         e[4 * k] = v.x; e[4 * k + 1] = v.y; e[4 * k + 2] = v.z; e[4 * k + 3] = v.w;
       }
       lp_stage_row<32>(tme + TC_A, e);
-      LP_TCG_HANDOFF(1 + grp, GT, leader, lp_issue_layer_part(tbase, TC_D, TC_A, w_och, w_ocl, 2, 2, 1024, 64, 16, wig); lp_tc_commit(bar));
+      LP_TCG_HANDOFF(1 + grp, GT, lp_elect_one(), lp_issue_layer_part(tbase, TC_D, TC_A, w_och, w_ocl, 2, 2, 1024, 64, 16, wig); lp_tc_commit(bar));
       LP_TCG_WAIT(bar, phase);
       lp_tmem_ld32u(tme + TC_D + 32, e);
       lp_tmem_zero<32>(tme + TC_D + 32);
@@ -495,7 +499,7 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
       lp_tc_fence_before();
       const bool full = LP_TC_EMPTY_FOLD ? (lp_bar_any(1 + grp, GT, hit) || probe) : (lp_bar_sync(1 + grp, GT), true);
       if (full) {
-      if (leader) {
+      if (lp_elect_one()) {
         lp_tc_fence_after();
         lp_issue_layer_part(tbase, TC_D, TC_A, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, 16, wig);
         lp_tc_commit(bar);
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
       lp_tmem_wait_st();
       lp_tc_fence_before();
       lp_bar_sync(1 + grp, GT);
-      if (leader) {
+      if (lp_elect_one()) {
         lp_tc_fence_after();
         lp_issue_layer_part(tbase, TC_D, TC_A, w_t1h, w_t1l, 2, 0, 512, 32, 16, wig);
         lp_tc_commit(bar);
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
       lp_tmem_wait_st();
       lp_tc_fence_before();
       lp_bar_sync(1 + grp, GT);
-      if (leader) {
+      if (lp_elect_one()) {
         lp_tc_fence_after();
         lp_issue_layer_part(tbase, TC_D, TC_A, w_och, w_ocl, 2, 0, 1024, 64, 16, wig);
         lp_tc_commit(bar);

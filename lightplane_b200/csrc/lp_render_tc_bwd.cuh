@@ -171,9 +171,12 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
   using I = Img<C>;
   using W = SImg<C>;
   LP_DYN_SMEM(unsigned char, sm);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool is_mlp = tid < 256;
-  const int grp = (tid & 255) / GT, s = tid % GT, wig = warp & 3;
+  // warp index through a broadcast shuffle: the compiler then knows that everything derived from it (group, tensor-memory
+  // and shared-memory operand addresses, mbarrier addresses) is warp-uniform and keeps it on the uniform datapath --
+  // otherwise every tcgen05.mma / commit / mbarrier operation is wrapped in an elect + R2UR.BROADCAST "waterfall" loop
+  const int tid = threadIdx.x, lane = tid & 31, warp = LP_WARP_UNIFORM(tid >> 5);
+  const bool is_mlp = warp < 8;
+  const int grp = (warp & 7) >> 2, s = tid % GT, wig = warp & 3;
   // mbarriers of group g at bars[8g + ..]: 0 round trips, 1 dW, 2 x0_full, 3 x0_free, 4 xt_full, 5 dx_full, 6 dx_free,
   // 7 first round trip of a slot (no group barrier precedes it, so it must not share a phase sequence with the others); bars[16] init
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + W::BARS);
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
   lp_tc_fence_before();
   __syncthreads();
   lp_tc_fence_after();
-  const unsigned tmem = *tmem_slot;
+  const unsigned tmem = LP_WARP_UNIFORM(*tmem_slot);
   if (tid == 0) {  // zero the dW accumulators: products of the (all-zero) gradient tiles with accumulate off
     const lp_kdesc_t a1 = lp_tc_mndesc_lo(gs + W::STK + W::CH_ONES * 2048), a2 = lp_tc_mndesc_lo(gs + W::STK),
                      dy = lp_tc_mndesc_lo(gs + W::DY), dyl = lp_tc_mndesc_lo(gs + W::DYL), ae = lp_tc_mndesc_lo(gs + W::STK + W::CH_H1 * 2048);
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
     // decoder group
     // =================================================================================================================
     if constexpr (LP_WS_REGS_MLP(C) > 128) LP_SETMAXNREG_INC(LP_WS_REGS_MLP(C));
-    const bool leader = lane == 0;  // lane 0 of each of the group's four warps issues its share of every product
+    // one elected lane (elect.sync) of each of the group's four warps issues its share of every product
     const int wi = wig;
     const float* F = reinterpret_cast<const float*>(sm + I::F32);
     const float4* ecb = reinterpret_cast<const float4*>(gs + W::ECB) + s;
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
 #define LP_ISSUE(A, WH, WL, KS, K0, NS, N, LO, WI) lp_issue_layer_part(tbase, ST_D, A, WH, WL, KS, K0, NS, N, LO, WI)
 #define LP_ISSUE_D(DC, A, WH, WL, KS, K0, NS, N, LO, WI) lp_issue_layer_part(tbase, DC, A, WH, WL, KS, K0, NS, N, LO, WI)
 #define LP_ISSUE_TF32(DC, A, W_, KS, K0, NS, N) lp_issue_tf32_part(tbase, DC, A, W_, KS, K0, NS, N, wi)
-#define LP_TC_HANDOFF(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, leader, ISSUE)
+#define LP_TC_HANDOFF(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, lp_elect_one(), ISSUE)
 #define LP_TC_WAIT() LP_TCG_WAIT(bar, phase)
 #define LP_TC_ROUND(ISSUE) LP_TC_HANDOFF(ISSUE) LP_TC_WAIT()
 
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         float raw = e_raw, lg0 = e_lg0, lg1 = e_lg1, lg2 = e_lg2;  // flag 0: every sample is empty -> the probe's decoder output
         if (flag == 1) {
           // ------------------------------ forward recompute ------------------------------
-          if (leader) {
+          if (lp_elect_one()) {
             lp_tc_fence_after();
             LP_ISSUE(ST_X, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, 16, wi);
             lp_tc_commit(bar0);
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           continue;
         }
         // ------------------------------ forward recompute ------------------------------
-        if (leader) {
+        if (lp_elect_one()) {
           lp_tc_fence_after();
           LP_ISSUE(ST_X, w_t0h, w_t0l, C / 16, 0, (C / 8) * 128, 32, 16, wi);
           lp_tc_commit(bar0);

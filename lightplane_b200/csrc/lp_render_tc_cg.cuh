@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(384, 1) lp_render_bwd_cg_kernel(LpRays R, LpMa
   const int num_tiles = (R.n + GT - 1) / GT;
   const int tot = M.S + M.S_inf;
 
-#define LP_CG_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, issuer, ISSUE) LP_TCG_WAIT(bar, phase)
+#define LP_CG_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, lp_elect_one(), ISSUE) LP_TCG_WAIT(bar, phase)
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
     const Ray1 me = lp_load_ray1(R, tile * GT + s, G.g[0].B);

@@ -98,7 +98,7 @@ LP_DEVICE void dp_load_enc(const LpRays& R, int q, float (&e)[32]) {
   }
 }
 
-#define LP_DP_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, issuer, ISSUE; lp_tc_commit(bar)) LP_TCG_WAIT(bar, phase)
+#define LP_DP_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, lp_elect_one(), ISSUE; lp_tc_commit(bar)) LP_TCG_WAIT(bar, phase)
 #define LP_DP_LD(v) lp_tmem_ld32u(tme + DT_D, v); lp_tmem_zero<32>(tme + DT_D)
 
 // ===========================================================================================

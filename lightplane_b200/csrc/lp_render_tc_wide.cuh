@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256, 1) lp_render_fwd_tcw_kernel(LpRays R, LpM
   const int num_tiles = (R.n + GT - 1) / GT;
   const int tot = M.S + M.S_inf;
 
-#define LP_W_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, issuer, ISSUE; lp_tc_commit(bar)) LP_TCG_WAIT(bar, phase)
+#define LP_W_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, lp_elect_one(), ISSUE; lp_tc_commit(bar)) LP_TCG_WAIT(bar, phase)
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
     const Ray1 me = lp_load_ray1(R, tile * GT + (tid % GT), G.g[0].B);
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256, 1) lp_render_bwd_tcw_kernel(LpRays R, LpM
   const int tot = M.S + M.S_inf;
   float bl0 = 0.f, bl1 = 0.f, bl2 = 0.f, bl3 = 0.f;  // last-layer bias gradients of this thread's samples (part 0 only)
 
-#define LP_WB_HANDOFF(ISSUE) LP_TCG_HANDOFF(1, GTH, issuer, ISSUE)
+#define LP_WB_HANDOFF(ISSUE) LP_TCG_HANDOFF(1, GTH, (warp < 4 && lp_elect_one()), ISSUE)
 #define LP_WB_WAIT() LP_TCG_WAIT(bar, phase)
 #define LP_WB_ROUND(ISSUE) LP_WB_HANDOFF(ISSUE) LP_WB_WAIT()
   // this part's 32 columns of the accumulator row

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(512, 1) lp_mlp_splat_fwd_tc_kernel(LpRays R, L
   const int num_tiles = (R.n + GT - 1) / GT;
   const int tot = M.S + M.S_inf;
 
-#define LP_SP_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, issuer, ISSUE; lp_tc_commit(bar)) LP_TCG_WAIT(bar, phase)
+#define LP_SP_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, lp_elect_one(), ISSUE; lp_tc_commit(bar)) LP_TCG_WAIT(bar, phase)
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
     const Ray1 me = lp_load_ray1(R, tile * GT + (tid % GT), OUT.g[0].B);
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(512, 1) lp_mlp_splat_bwd_tc_kernel(LpRays R, L
   const int num_tiles = (R.n + GT - 1) / GT;
   const int tot = M.S + M.S_inf;
 
-#define LP_SP_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, issuer, ISSUE) LP_TCG_WAIT(bar, phase)
+#define LP_SP_ROUND(ISSUE) LP_TCG_HANDOFF(1 + grp, GT, lp_elect_one(), ISSUE) LP_TCG_WAIT(bar, phase)
 
   for (int tile = blockIdx.x * ngroups + grp; tile < num_tiles; tile += gridDim.x * ngroups) {
     const Ray1 me = lp_load_ray1(R, tile * GT + s, GG.g[0].B);

@@ -255,6 +255,7 @@ static inline void lp_hs_mbar_arrive(unsigned long long* bar) {
   } while (!a.compare_exchange_weak(o, n, std::memory_order_acq_rel));
 }
 static inline void lp_mbar_arrive(unsigned long long* bar) { lp_hs_mbar_arrive(bar); }
+static inline bool lp_elect_one() { return lp_hostsim::g_ctx->lane == 0; }
 #define LP_SETMAXNREG_INC(n)
 #define LP_SETMAXNREG_DEC(n)
 static inline void lp_fence_async_smem() { std::atomic_thread_fence(std::memory_order_seq_cst); }
