@@ -73,6 +73,22 @@ static int lp_make_gridset(const lp_grid_list* in, LpGridSet* out, const char* n
     g.base = base;
     base += (long long)g.B * g.D * g.H * g.W * in->channels;
   }
+  // Triplane: exactly one XY, one XZ and one YZ plane with consistent axis sizes.  The entries are put in that order
+  // (each keeps its own base offset, so the order of the table is free) and the kernels take their fast path.
+  if (out->n == 3) {
+    int at[3] = {-1, -1, -1};
+    for (int i = 0; i < 3; ++i) {
+      const int k = out->g[i].kind;
+      if (k == LP_PLANE_XY) at[0] = i; else if (k == LP_PLANE_XZ) at[1] = i; else if (k == LP_PLANE_YZ) at[2] = i;
+    }
+    if (at[0] >= 0 && at[1] >= 0 && at[2] >= 0) {
+      const LpGrid xy = out->g[at[0]], xz = out->g[at[1]], yz = out->g[at[2]];
+      if (xy.W == xz.W && xy.H == yz.H && xz.D == yz.D && xy.W > 1 && xy.H > 1 && xz.D > 1) {
+        out->g[0] = xy; out->g[1] = xz; out->g[2] = yz;
+        out->tri = 1;
+      }
+    }
+  }
   return LP_OK;
 }
 

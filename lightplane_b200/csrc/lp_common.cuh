@@ -23,6 +23,8 @@ struct LpGridSet {
   float* data;  // flat [rows, C]
   int n;
   int C;
+  int tri;      // 1: g[0..2] are the XY, XZ, YZ planes of one W x H x D volume, in this order (the kernels' triplane fast path)
+  int pad_;
   LpGrid g[LP_MAX_GRIDS];
 };
 

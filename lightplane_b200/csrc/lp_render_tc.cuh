@@ -254,6 +254,38 @@ LP_DEVICE int lp_taps_i32(const LpGrid& g, int C, int b, float x, float y, float
   return 4;
 }
 
+// ---- triplane fast path (LpGridSet::tri: the grids are exactly the XY, XZ and YZ planes of one W x H x D volume) ----
+// The three planes share their axes: the index, fraction, clamped corners and weights of x, y and z are worked out ONCE
+// per sample (the generic loop does it twice per plane, behind a run-time switch on the grid kind, before it can tell
+// that a plane is missed), a plane is hit iff both of its axes are in range, and its taps are products / sums of the
+// two axes' values -- the same numbers as lp_taps_i32 gives.
+struct LpAxis {
+  int i0, c0, c1;   // unclamped base cell, clamped corner indices
+  float w0, w1;     // corner weights (0 outside the grid)
+  bool ok;          // at least one corner inside
+};
+LP_DEVICE LpAxis lp_axis_pre(float p, int size) {
+  LpAxis a;
+  float fr;
+  lp_axis_i(p, size, a.i0, fr);
+  a.ok = (unsigned)(a.i0 + 1) <= (unsigned)size;
+  lp_corner_i(a.i0, fr, size, a.w0, a.w1, a.c0, a.c1);
+  return a;
+}
+LP_DEVICE LpAxis lp_axis_sel(bool first, const LpAxis& a, const LpAxis& b) {
+  LpAxis r;
+  r.i0 = first ? a.i0 : b.i0; r.c0 = first ? a.c0 : b.c0; r.c1 = first ? a.c1 : b.c1;
+  r.w0 = first ? a.w0 : b.w0; r.w1 = first ? a.w1 : b.w1; r.ok = first ? a.ok : b.ok;
+  return r;
+}
+// the four taps of a plane (fast axis u of size U, slow axis v) whose element offset starts at `bbase`
+LP_DEVICE void lp_plane_taps_pre(int bbase, int U, int C, const LpAxis& au, const LpAxis& av, int* off, float* w) {
+  off[0] = bbase + (av.c0 * U + au.c0) * C; w[0] = au.w0 * av.w0;
+  off[1] = bbase + (av.c0 * U + au.c1) * C; w[1] = au.w1 * av.w0;
+  off[2] = bbase + (av.c1 * U + au.c0) * C; w[2] = au.w0 * av.w1;
+  off[3] = bbase + (av.c1 * U + au.c1) * C; w[3] = au.w1 * av.w1;
+}
+
 constexpr int GT = 128;  // threads = rays per group (the MMA's M)
 
 // Ray handled by thread s of ray tile `tile`.  Default: 128 consecutive rays.  With the image-width hint
@@ -364,7 +396,7 @@ LP_DEVICE void lp_issue_layer_part(unsigned tbase, int d_col, int a_col, lp_kdes
 // the owner thread samples all C channels of its sample point into registers
 // (CW channels starting at ch0: a sample's channels may be split over several threads)
 // Returns whether the sample touches any grid at all (false: acc is exactly zero).
-template <int C, int CW = C>
+template <int C, int CW = C, bool TRI = true>
 LP_DEVICE bool lp_gather_regs(const LpGridSet& G, int b, float x, float y, float z, float oob, float (&acc)[CW], int ch0 = 0) {
   bool hit = false;
 #pragma unroll
@@ -373,6 +405,30 @@ LP_DEVICE bool lp_gather_regs(const LpGridSet& G, int b, float x, float y, float
   acc[0] = x * y + z;
   return true;
 #endif
+  if (TRI && G.tri) {  // XY, XZ, YZ planes of one volume (lp_cabi.cu lp_make_gridset): axes once, planes unrolled
+    const int W = G.g[0].W, Hh = G.g[0].H, Dd = G.g[1].D;
+    const LpAxis ax = lp_axis_pre(x, W), ay = lp_axis_pre(y, Hh), az = lp_axis_pre(z, Dd);
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const LpAxis& au = p == 2 ? ay : ax;
+      const LpAxis& av = p == 0 ? ay : az;
+      if (!(au.ok && av.ok)) continue;  // the sample misses this plane
+      hit = true;
+      const int U = p == 2 ? Hh : W, V = p == 0 ? Hh : Dd;
+      int off[4];
+      float w[4];
+      lp_plane_taps_pre((int)G.g[p].base + b * U * V * C, U, C, au, av, off, w);
+#pragma unroll
+      for (int tp = 0; tp < 4; ++tp) {
+#pragma unroll
+        for (int k = 0; k < CW / 4; ++k) {
+          const float4 v = lp_ldg4(G.data + off[tp] + ch0 + 4 * k);
+          acc[4 * k] = fmaf(w[tp], v.x, acc[4 * k]); acc[4 * k + 1] = fmaf(w[tp], v.y, acc[4 * k + 1]);
+          acc[4 * k + 2] = fmaf(w[tp], v.z, acc[4 * k + 2]); acc[4 * k + 3] = fmaf(w[tp], v.w, acc[4 * k + 3]);
+        }
+      }
+    }
+  } else
   for (int gi = 0; gi < G.n; ++gi) {
     int off[8];
     float w[8];
@@ -747,7 +803,64 @@ LP_DEVICE void lp_red_row(float* p, const float (&v)[CW]) {
 #pragma unroll
   for (int k = 0; k < CW / 4; ++k) lp_red_add4(p + 4 * k, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
-template <int C>
+// one grid's share of lp_splat_quad: this lane's taps (off, w; nt == 0: none) with footprint key `fkey`; NT = taps
+// the unrolled passes cover (4: planes only), ntw = taps of this grid (warp-uniform)
+template <int CW, int NT>
+LP_DEVICE void lp_splat_quad_grid(float* grad, int q, int qbase, int nt, int fkey, int ntw, int (&off)[NT], float (&w)[NT],
+                                  const float (&blk)[4][CW]) {
+  if (!__any_sync(LP_FULL_MASK, nt != 0)) return;  // nobody in the warp touches this grid
+  if (nt == 0) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) { off[t] = 0; w[t] = 0.f; }
+  }
+  const int key = nt != 0 ? fkey : -1;  // -1: no contribution
+  int kA = max(key, __shfl_xor_sync(LP_FULL_MASK, key, 1));
+  kA = max(kA, __shfl_xor_sync(LP_FULL_MASK, kA, 2));
+  const bool inA = key >= 0 && key == kA;  // merged pass: every sample of the quad standing on footprint kA
+  const unsigned mA = (__ballot_sync(LP_FULL_MASK, inA) >> qbase) & 15u;
+  if (__any_sync(LP_FULL_MASK, mA != 0)) {
+    const int owner = qbase + (mA ? __ffs((int)mA) - 1 : 0);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (t < ntw) {
+        const int o = __shfl_sync(LP_FULL_MASK, off[t], owner);
+        float v[CW];
+#pragma unroll
+        for (int i = 0; i < CW; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float wj = __shfl_sync(LP_FULL_MASK, inA ? w[t] : 0.f, qbase + j);
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] = fmaf(wj, blk[j][i], v[i]);
+        }
+        if (mA) lp_red_row<CW>(grad + o + q * CW, v);
+      }
+    }
+  }
+  // samples of the quad on another footprint: one pass each (rare for neighbouring pixels)
+  const bool left = key >= 0 && !inA;
+  const unsigned mL = __ballot_sync(LP_FULL_MASK, left);
+  if (mL == 0) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (!((mL >> j) & 0x11111111u)) continue;  // no quad has a leftover in position j
+    const bool need = (mL >> (qbase + j)) & 1u;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (t < ntw) {
+        const int o = __shfl_sync(LP_FULL_MASK, off[t], qbase + j);
+        const float wj = __shfl_sync(LP_FULL_MASK, w[t], qbase + j);
+        if (need) {
+          float v[CW];
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] = wj * blk[j][i];
+          lp_red_row<CW>(grad + o + q * CW, v);
+        }
+      }
+    }
+  }
+}
+template <int C, bool TRI = true>
 LP_DEVICE void lp_splat_quad(const LpGridSet& G, float* grad, int b, float x, float y, float z, bool valid, const float (&d)[C]) {
   constexpr int CW = C / 4;
   const int lane = threadIdx.x & 31, q = lane & 3, qbase = lane & ~3;
@@ -757,63 +870,27 @@ LP_DEVICE void lp_splat_quad(const LpGridSet& G, float* grad, int b, float x, fl
 #pragma unroll
     for (int i = 0; i < CW; ++i) blk[k][i] = valid ? d[k * CW + i] : 0.f;
   lp_quad_transpose<CW>(blk, q);
+  if (TRI && G.tri) {  // triplane: axes once, one (run-time) loop over the three planes with four-tap passes
+    const int W = G.g[0].W, Hh = G.g[0].H, Dd = G.g[1].D;
+    const LpAxis ax = lp_axis_pre(x, W), ay = lp_axis_pre(y, Hh), az = lp_axis_pre(z, Dd);
+#pragma unroll 1
+    for (int p = 0; p < 3; ++p) {
+      const LpAxis au = lp_axis_sel(p == 2, ay, ax), av = lp_axis_sel(p == 0, ay, az);
+      const int U = p == 2 ? Hh : W, V = p == 0 ? Hh : Dd;
+      const int nt = valid && au.ok && av.ok ? 4 : 0;
+      int off[4];
+      float w[4];
+      lp_plane_taps_pre((int)G.g[p].base + b * U * V * C, U, C, au, av, off, w);
+      lp_splat_quad_grid<CW, 4>(grad, q, qbase, nt, (b * (V + 3) + av.i0 + 2) * (U + 3) + au.i0 + 2, 4, off, w, blk);
+    }
+    return;
+  }
   for (int gi = 0; gi < G.n; ++gi) {
     int off[8];
     float w[8];
     int fkey = -1;
     const int nt = valid ? lp_taps_i32(G.g[gi], C, b, x, y, z, off, w, &fkey) : 0;
-    if (!__any_sync(LP_FULL_MASK, nt != 0)) continue;  // nobody in the warp touches this grid
-    if (nt == 0) {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) { off[t] = 0; w[t] = 0.f; }
-    }
-    const int ntw = G.g[gi].kind == LP_VOXEL ? 8 : 4;  // uniform: taps of this grid
-    const int key = nt != 0 ? fkey : -1;  // -1: no contribution
-    int kA = max(key, __shfl_xor_sync(LP_FULL_MASK, key, 1));
-    kA = max(kA, __shfl_xor_sync(LP_FULL_MASK, kA, 2));
-    const bool inA = key >= 0 && key == kA;  // merged pass: every sample of the quad standing on footprint kA
-    const unsigned mA = (__ballot_sync(LP_FULL_MASK, inA) >> qbase) & 15u;
-    if (__any_sync(LP_FULL_MASK, mA != 0)) {
-      const int owner = qbase + (mA ? __ffs((int)mA) - 1 : 0);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        if (t < ntw) {
-          const int o = __shfl_sync(LP_FULL_MASK, off[t], owner);
-          float v[CW];
-#pragma unroll
-          for (int i = 0; i < CW; ++i) v[i] = 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float wj = __shfl_sync(LP_FULL_MASK, inA ? w[t] : 0.f, qbase + j);
-#pragma unroll
-            for (int i = 0; i < CW; ++i) v[i] = fmaf(wj, blk[j][i], v[i]);
-          }
-          if (mA) lp_red_row<CW>(grad + o + q * CW, v);
-        }
-      }
-    }
-    // samples of the quad on another footprint: one pass each (rare for neighbouring pixels)
-    const bool left = key >= 0 && !inA;
-    const unsigned mL = __ballot_sync(LP_FULL_MASK, left);
-    if (mL == 0) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (!((mL >> j) & 0x11111111u)) continue;  // no quad has a leftover in position j
-      const bool need = (mL >> (qbase + j)) & 1u;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        if (t < ntw) {
-          const int o = __shfl_sync(LP_FULL_MASK, off[t], qbase + j);
-          const float wj = __shfl_sync(LP_FULL_MASK, w[t], qbase + j);
-          if (need) {
-            float v[CW];
-#pragma unroll
-            for (int i = 0; i < CW; ++i) v[i] = wj * blk[j][i];
-            lp_red_row<CW>(grad + o + q * CW, v);
-          }
-        }
-      }
-    }
+    lp_splat_quad_grid<CW, 8>(grad, q, qbase, nt, fkey, G.g[gi].kind == LP_VOXEL ? 8 : 4, off, w, blk);
   }
 }
 

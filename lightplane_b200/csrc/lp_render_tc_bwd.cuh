@@ -151,6 +151,14 @@ LP_DEVICE void lp_ws_issue_encw_part(unsigned tmem, unsigned char* gs, int wi) {
 //                       compositing gradient has one call site: -2.5 ms (decoder warps were 30 % instruction-fetch stalled)
 //   LP_MEM_SINGLE_LOOP  1: one slot loop with single gather / stage / scatter sites in the memory role: +5 ms -- the
 //                       compiler's unrolling of the step loop overlaps one slot's scatter with the next slot's gather
+// triplane fast path (lp_render_tc.cuh) in the memory role's gather / scatter: off -- its per-axis state costs the 88-register
+// memory threads more spills than the shared index arithmetic saves (measured: backward 44.2 -> 45.0 ms with either; all-in-volume 73.6 -> 69.5 ms with the scatter's)
+#ifndef LP_BWD_TRI_GATHER
+#define LP_BWD_TRI_GATHER false
+#endif
+#ifndef LP_BWD_TRI_SCATTER
+#define LP_BWD_TRI_SCATTER false
+#endif
 #ifndef LP_MLP_COMPACT
 #define LP_MLP_COMPACT 1
 #endif
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           if (SCAF && !lp_bar_any(3 + grp, GT, occ != 0.f)) {
             flag = 2;  // nobody's sample is occupied: the slot changes nothing
           } else {
-            const bool hit = lp_gather_regs<C>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
+            const bool hit = lp_gather_regs<C, C, LP_BWD_TRI_GATHER>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
             flag = lp_bar_any(3 + grp, GT, hit) ? 1 : 0;
             any_empty |= flag == 0;
           }
@@ -297,7 +305,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           if (pend_scatter) {  // (warp-uniform) quad-transposed, footprint-merging reduction into the grid gradient
 #pragma unroll
             for (int c = 0; c < C; ++c) dxp[c] *= prev.oob;
-            lp_splat_quad<C>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, me.active && prev.oob != 0.f, dxp);
+            lp_splat_quad<C, LP_BWD_TRI_SCATTER>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, me.active && prev.oob != 0.f, dxp);
           }
           pend = false;
         }
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         if (scatter) {  // (warp-uniform) quad-transposed, footprint-merging reduction into the grid gradient
 #pragma unroll
           for (int c = 0; c < C; ++c) dxp[c] *= prev.oob;
-          lp_splat_quad<C>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, me.active && prev.oob != 0.f, dxp);
+          lp_splat_quad<C, LP_BWD_TRI_SCATTER>(G, io.g_grid, me.b, prev.x, prev.y, prev.z, me.active && prev.oob != 0.f, dxp);
         }
       };
       // publish one slot: operand row (full slots) into tensor memory, flag + occupancy into shared memory
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           continue;
         }
         float x0[C];
-        const bool hit = lp_gather_regs<C>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
+        const bool hit = lp_gather_regs<C, C, LP_BWD_TRI_GATHER>(G, me.b, cur.x, cur.y, cur.z, cur.oob, x0);
         const bool full = lp_bar_any(3 + grp, GT, hit);
         any_empty |= !full;
         publish(full ? 1 : 0, x0, occ, true);
