@@ -322,5 +322,38 @@ LP_DEVICE bool lp_bar_any(int id, int nthreads, bool pred) {
 }
 #endif  // !LP_HOSTSIM
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: `*.f32x2`): one issue slot for two IEEE fp32 operations, each
+// rounded exactly like its scalar form (tools/ubench_f32x2.cu: an FFMA2 occupies the FMA pipe for two cycles but the
+// scheduler for one -- the tensor-core kernels are bound by issue slots, not by the FMA pipe).
+LP_DEVICE float2 lp_fma2(float2 a, float2 b, float2 c) {
+#if defined(LP_HOSTSIM)
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#else
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+#endif
+}
+#if defined(LP_HOSTSIM)
+LP_DEVICE float2 lp_add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+LP_DEVICE float2 lp_sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+LP_DEVICE float2 lp_mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#else
+#define LP_F32X2_BINARY(NAME, OP)                                                                                         \
+  LP_DEVICE float2 NAME(float2 a, float2 b) {                                                                             \
+    float2 d;                                                                                                             \
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t" OP ".rn.f32x2 rd, ra, rb;\n\t"       \
+        "mov.b64 {%0, %1}, rd;\n\t}" : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                    \
+    return d;                                                                                                             \
+  }
+LP_F32X2_BINARY(lp_add2, "add")
+LP_F32X2_BINARY(lp_sub2, "sub")
+LP_F32X2_BINARY(lp_mul2, "mul")
+#undef LP_F32X2_BINARY
+#endif
+LP_DEVICE float2 lp_f2(float x, float y) { return make_float2(x, y); }
+
 // Broadcast of lane 0's value: tells the compiler the value is warp-uniform (it may then live in uniform registers).
 #define LP_WARP_UNIFORM(x) __shfl_sync(0xffffffffu, (x), 0)

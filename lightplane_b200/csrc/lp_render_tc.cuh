@@ -308,7 +308,7 @@ struct Img {
   static constexpr int T1_LO = T1_HI + 2048;
   static constexpr int OC_HI = T1_LO + 2048;        // [64 out: opacity hidden | colour hidden][64 in: trunk | encoding]
   static constexpr int OC_LO = OC_HI + 8192;
-  static constexpr int F32 = OC_LO + 8192;          // fp32: b_t0 b_t1 b_o0 b_c0 [4][32] | wo1[32] | Wc1[32][4] | b_last[4]
+  static constexpr int F32 = OC_LO + 8192;          // fp32: b_t0 b_t1 b_o0 b_c0 [4][32] | wo1[32] | Wc1 as [16 row pairs][4 outputs][2 rows] | b_last[4]
   static constexpr int FB = 0, FWO = 128, FWC = 160, FBL = 288, NF = 292;
   static constexpr int FWD_END = F32 + NF * 4;
 };
@@ -343,24 +343,126 @@ LP_DEVICE void lp_build_img(unsigned char* sm, const float* __restrict__ P, cons
     F[I::FB + 64 + e] = P[o0.b_off + e];
     F[I::FB + 96 + e] = P[c0.b_off + e];
     F[I::FWO + e] = P[o1.w_off + e * o1.N];
-    for (int c = 0; c < 4; ++c) F[I::FWC + 4 * e + c] = c < D.n_feat ? P[c1.w_off + e * c1.N + c] : 0.f;
+    for (int c = 0; c < 4; ++c) F[I::FWC + 8 * (e >> 1) + 2 * c + (e & 1)] = c < D.n_feat ? P[c1.w_off + e * c1.N + c] : 0.f;  // pair layout, see Img
   }
   if (tid < 4) F[I::FBL + tid] = tid == 3 ? P[o1.b_off] : (tid < D.n_feat ? P[c1.b_off + tid] : 0.f);
 }
 
 // x = hi + lo with hi = x truncated to bf16 and lo = bf16_rn(x - hi): two values -> one packed word each
+template <bool PK = true>
 LP_DEVICE void lp_split2(float x0, float x1, unsigned& hi, unsigned& lo) {
   hi = __byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632);
-  lo = lp_pack_bf16x2(x0 - __uint_as_float(__float_as_uint(x0) & 0xffff0000u), x1 - __uint_as_float(__float_as_uint(x1) & 0xffff0000u));
+  const float t0 = __uint_as_float(__float_as_uint(x0) & 0xffff0000u), t1 = __uint_as_float(__float_as_uint(x1) & 0xffff0000u);
+  if constexpr (PK) {
+    const float2 r = lp_sub2(lp_f2(x0, x1), lp_f2(t0, t1));
+    lo = lp_pack_bf16x2(r.x, r.y);
+  } else {
+    lo = lp_pack_bf16x2(x0 - t0, x1 - t1);
+  }
 }
 // split a row of N values and store it as this thread's row of the A operand (hi at a_col, lo at a_col + LO)
-template <int N, int LO = 16>
+template <int N, int LO = 16, bool PK = true>
 LP_DEVICE void lp_stage_row(unsigned taddr_a, const float (&x)[N]) {
   unsigned hi[N / 2], lo[N / 2];
 #pragma unroll
-  for (int j = 0; j < N / 2; ++j) lp_split2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+  for (int j = 0; j < N / 2; ++j) lp_split2<PK>(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
   lp_tmem_st<N / 2>(taddr_a, hi);
   lp_tmem_st<N / 2>(taddr_a + LO, lo);
+}
+
+// ---- decoder epilogue arithmetic on packed fp32 pairs (same roundings as the scalar forms; lp_platform.cuh) ----
+// v[j] = max(v[j] + bias[j], 0) for a row of N accumulator values (bias in shared memory, 16-byte aligned)
+template <int N, bool PK = true>
+LP_DEVICE void lp_bias_relu(float (&v)[N], const float* bias) {
+#pragma unroll
+  for (int k = 0; k < N / 4; ++k) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * k);
+    if constexpr (!PK) {
+      v[4 * k] = fmaxf(v[4 * k] + b.x, 0.f); v[4 * k + 1] = fmaxf(v[4 * k + 1] + b.y, 0.f);
+      v[4 * k + 2] = fmaxf(v[4 * k + 2] + b.z, 0.f); v[4 * k + 3] = fmaxf(v[4 * k + 3] + b.w, 0.f);
+      continue;
+    }
+    const float2 lo = lp_add2(lp_f2(v[4 * k], v[4 * k + 1]), lp_f2(b.x, b.y)), hi = lp_add2(lp_f2(v[4 * k + 2], v[4 * k + 3]), lp_f2(b.z, b.w));
+    v[4 * k] = fmaxf(lo.x, 0.f); v[4 * k + 1] = fmaxf(lo.y, 0.f); v[4 * k + 2] = fmaxf(hi.x, 0.f); v[4 * k + 3] = fmaxf(hi.y, 0.f);
+  }
+}
+// opacity head: bias + sum_j h[j] * wo[j], even and odd rows in the two halves of one packed accumulator
+template <bool PK = true>
+LP_DEVICE float lp_head_opacity(const float (&h)[32], const float* wo, float bias) {
+  if constexpr (!PK) {
+    float r0 = bias, r1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) { r0 = fmaf(h[j], wo[j], r0); r1 = fmaf(h[j + 1], wo[j + 1], r1); }
+    return r0 + r1;
+  }
+  float2 r = lp_f2(bias, 0.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 w = *reinterpret_cast<const float4*>(wo + 4 * k);
+    r = lp_fma2(lp_f2(h[4 * k], h[4 * k + 1]), lp_f2(w.x, w.y), r);
+    r = lp_fma2(lp_f2(h[4 * k + 2], h[4 * k + 3]), lp_f2(w.z, w.w), r);
+  }
+  return r.x + r.y;
+}
+// colour head (3 outputs): weights in the image's pair layout [row pair][output][row parity]
+template <bool PK = true>
+LP_DEVICE void lp_head_colour(const float (&h)[32], const float* wc, const float* bias, float& lg0, float& lg1, float& lg2) {
+  if constexpr (!PK) {
+    float a0 = bias[0], a1 = bias[1], a2 = bias[2], b0 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+      const float4 wa = *reinterpret_cast<const float4*>(wc + 8 * p), wb = *reinterpret_cast<const float4*>(wc + 8 * p + 4);
+      a0 = fmaf(h[2 * p], wa.x, a0); a1 = fmaf(h[2 * p], wa.z, a1); a2 = fmaf(h[2 * p], wb.x, a2);
+      b0 = fmaf(h[2 * p + 1], wa.y, b0); b1 = fmaf(h[2 * p + 1], wa.w, b1); b2 = fmaf(h[2 * p + 1], wb.y, b2);
+    }
+    lg0 = a0 + b0; lg1 = a1 + b1; lg2 = a2 + b2;
+    return;
+  }
+  float2 a0 = lp_f2(bias[0], 0.f), a1 = lp_f2(bias[1], 0.f), a2 = lp_f2(bias[2], 0.f);
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const float4 wa = *reinterpret_cast<const float4*>(wc + 8 * p), wb = *reinterpret_cast<const float4*>(wc + 8 * p + 4);
+    const float2 hp = lp_f2(h[2 * p], h[2 * p + 1]);
+    a0 = lp_fma2(hp, lp_f2(wa.x, wa.y), a0);
+    a1 = lp_fma2(hp, lp_f2(wa.z, wa.w), a1);
+    a2 = lp_fma2(hp, lp_f2(wb.x, wb.y), a2);
+  }
+  lg0 = a0.x + a0.y; lg1 = a1.x + a1.y; lg2 = a2.x + a2.y;
+}
+// backward of the two heads: d_ho[j] = g_raw * wo[j];  d_hc[j] = dl0 * Wc[j][0] + dl1 * Wc[j][1] + dl2 * Wc[j][2]
+template <bool PK = true>
+LP_DEVICE void lp_head_opacity_bwd(float (&d)[32], const float* wo, float g_raw) {
+  if constexpr (!PK) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) d[j] = g_raw * wo[j];
+    return;
+  }
+  const float2 g = lp_f2(g_raw, g_raw);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 w = *reinterpret_cast<const float4*>(wo + 4 * k);
+    const float2 lo = lp_mul2(g, lp_f2(w.x, w.y)), hi = lp_mul2(g, lp_f2(w.z, w.w));
+    d[4 * k] = lo.x; d[4 * k + 1] = lo.y; d[4 * k + 2] = hi.x; d[4 * k + 3] = hi.y;
+  }
+}
+template <bool PK = true>
+LP_DEVICE void lp_head_colour_bwd(float (&d)[32], const float* wc, float dl0, float dl1, float dl2) {
+  if constexpr (!PK) {
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+      const float4 wa = *reinterpret_cast<const float4*>(wc + 8 * p), wb = *reinterpret_cast<const float4*>(wc + 8 * p + 4);
+      d[2 * p] = fmaf(dl0, wa.x, fmaf(dl1, wa.z, dl2 * wb.x));
+      d[2 * p + 1] = fmaf(dl0, wa.y, fmaf(dl1, wa.w, dl2 * wb.y));
+    }
+    return;
+  }
+  const float2 g0 = lp_f2(dl0, dl0), g1 = lp_f2(dl1, dl1), g2 = lp_f2(dl2, dl2);
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const float4 wa = *reinterpret_cast<const float4*>(wc + 8 * p), wb = *reinterpret_cast<const float4*>(wc + 8 * p + 4);
+    const float2 r = lp_fma2(g0, lp_f2(wa.x, wa.y), lp_fma2(g1, lp_f2(wa.z, wa.w), lp_mul2(g2, lp_f2(wb.x, wb.y))));
+    d[2 * p] = r.x; d[2 * p + 1] = r.y;
+  }
 }
 
 // per-group tensor-memory columns (forward): A hi 0..15 / lo 16..31, D 32..95
@@ -420,11 +522,12 @@ LP_DEVICE bool lp_gather_regs(const LpGridSet& G, int b, float x, float y, float
       lp_plane_taps_pre((int)G.g[p].base + b * U * V * C, U, C, au, av, off, w);
 #pragma unroll
       for (int tp = 0; tp < 4; ++tp) {
+        const float2 wp = lp_f2(w[tp], w[tp]);
 #pragma unroll
         for (int k = 0; k < CW / 4; ++k) {
           const float4 v = lp_ldg4(G.data + off[tp] + ch0 + 4 * k);
-          acc[4 * k] = fmaf(w[tp], v.x, acc[4 * k]); acc[4 * k + 1] = fmaf(w[tp], v.y, acc[4 * k + 1]);
-          acc[4 * k + 2] = fmaf(w[tp], v.z, acc[4 * k + 2]); acc[4 * k + 3] = fmaf(w[tp], v.w, acc[4 * k + 3]);
+          const float2 lo = lp_fma2(wp, lp_f2(v.x, v.y), lp_f2(acc[4 * k], acc[4 * k + 1])), hi = lp_fma2(wp, lp_f2(v.z, v.w), lp_f2(acc[4 * k + 2], acc[4 * k + 3]));
+          acc[4 * k] = lo.x; acc[4 * k + 1] = lo.y; acc[4 * k + 2] = hi.x; acc[4 * k + 3] = hi.y;
         }
       }
     }
@@ -565,8 +668,7 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
       lp_tc_fence_after();
       lp_tmem_ld32u(tme + TC_D, v);
       lp_tmem_zero<32>(tme + TC_D);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + j], 0.f);
+      lp_bias_relu<32>(v, F + I::FB);
       lp_stage_row<32>(tme + TC_A, v);
       // ---- trunk layer 1 ----
       lp_tmem_wait_st();
@@ -581,8 +683,7 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
       lp_tc_fence_after();
       lp_tmem_ld32u(tme + TC_D, v);
       lp_tmem_zero<32>(tme + TC_D);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + 32 + j], 0.f);
+      lp_bias_relu<32>(v, F + I::FB + 32);
       lp_stage_row<32>(tme + TC_A, v);
       // ---- opacity + colour hidden layers: trunk (K = 32) x [64 outputs]; the encoding's share comes from `ecb` ----
       lp_tmem_wait_st();
@@ -597,32 +698,19 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
       lp_tc_fence_after();
       // ---- output layer (4 wide) on the CUDA cores, exact fp32 (two partial sums per output, as in the backward) ----
       {
-        float r0 = F[I::FBL + 3], r1 = 0.f;
         lp_tmem_ld32u(tme + TC_D, v);
         lp_tmem_zero<32>(tme + TC_D);
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          r0 = fmaf(fmaxf(v[j] + F[I::FB + 64 + j], 0.f), F[I::FWO + j], r0);
-          r1 = fmaf(fmaxf(v[j + 1] + F[I::FB + 64 + j + 1], 0.f), F[I::FWO + j + 1], r1);
-        }
-        raw = r0 + r1;
-        float a0 = F[I::FBL], a1 = F[I::FBL + 1], a2 = F[I::FBL + 2], b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        lp_bias_relu<32>(v, F + I::FB + 64);
+        raw = lp_head_opacity(v, F + I::FWO, F[I::FBL + 3]);
         lp_tmem_ld32u(tme + TC_D + 32, v);
         lp_tmem_zero<32>(tme + TC_D + 32);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 8; ++k) {  // enc x Wc0 + b (per ray) stands in for the bias
           const float4 eb = ecb[k * GT];
-          v[4 * k] = fmaxf(v[4 * k] + eb.x, 0.f); v[4 * k + 1] = fmaxf(v[4 * k + 1] + eb.y, 0.f);
-          v[4 * k + 2] = fmaxf(v[4 * k + 2] + eb.z, 0.f); v[4 * k + 3] = fmaxf(v[4 * k + 3] + eb.w, 0.f);
+          const float2 lo = lp_add2(lp_f2(v[4 * k], v[4 * k + 1]), lp_f2(eb.x, eb.y)), hi = lp_add2(lp_f2(v[4 * k + 2], v[4 * k + 3]), lp_f2(eb.z, eb.w));
+          v[4 * k] = fmaxf(lo.x, 0.f); v[4 * k + 1] = fmaxf(lo.y, 0.f); v[4 * k + 2] = fmaxf(hi.x, 0.f); v[4 * k + 3] = fmaxf(hi.y, 0.f);
         }
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float4 w0 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
-          const float4 w1 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j + 4);
-          a0 = fmaf(v[j], w0.x, a0); a1 = fmaf(v[j], w0.y, a1); a2 = fmaf(v[j], w0.z, a2);
-          b0 = fmaf(v[j + 1], w1.x, b0); b1 = fmaf(v[j + 1], w1.y, b1); b2 = fmaf(v[j + 1], w1.z, b2);
-        }
-        lg0 = a0 + b0; lg1 = a1 + b1; lg2 = a2 + b2;
+        lp_head_colour(v, F + I::FWC, F + I::FBL, lg0, lg1, lg2);
       }
       if (probe) { e_raw = raw; e_lg0 = lg0; e_lg1 = lg1; e_lg2 = lg2; continue; }
       } else {

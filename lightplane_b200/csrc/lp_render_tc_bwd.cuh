@@ -159,6 +159,20 @@ LP_DEVICE void lp_ws_issue_encw_part(unsigned tmem, unsigned char* gs, int wi) {
 #ifndef LP_BWD_TRI_SCATTER
 #define LP_BWD_TRI_SCATTER false
 #endif
+// packed fp32 pairs (lp_platform.cuh), per use.  Measured (backward ms, headline): none 44.09; decoder split only 43.61, bias only 43.71,
+// output heads only 43.27, all three 42.64; all three + the memory role's split 47.67
+#ifndef LP_BWD_PK_MEM  // the memory role's x0 split stays scalar: packed, its 88-register threads run the whole backward 5 ms slower
+#define LP_BWD_PK_MEM false
+#endif
+#ifndef LP_BWD_PK_SPLIT
+#define LP_BWD_PK_SPLIT true
+#endif
+#ifndef LP_BWD_PK_BIAS
+#define LP_BWD_PK_BIAS true
+#endif
+#ifndef LP_BWD_PK_HEADS
+#define LP_BWD_PK_HEADS true
+#endif
 #ifndef LP_MLP_COMPACT
 #define LP_MLP_COMPACT 1
 #endif
@@ -282,7 +296,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           if (n_slot > 0) lp_mbar_wait(x0_free, (n_slot - 1) & 1);
           if (flag == 1) {
             lp_tc_fence_after();
-            lp_stage_row<C, 16>(tme + ST_X, x0);
+            lp_stage_row<C, 16, LP_BWD_PK_MEM>(tme + ST_X, x0);
             lp_tmem_wait_st();
             lp_tc_fence_before();
           }
@@ -352,7 +366,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         if (n_slot > 0) lp_mbar_wait(x0_free, (n_slot - 1) & 1);
         if (flag == 1) {
           lp_tc_fence_after();
-          lp_stage_row<C, 16>(tme + ST_X, x0);
+          lp_stage_row<C, 16, LP_BWD_PK_MEM>(tme + ST_X, x0);
           lp_tmem_wait_st();
           lp_tc_fence_before();
         }
@@ -447,7 +461,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           const float4 t = __ldg(e4 + k);
           v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
         }
-        lp_stage_row<32, 32>(tme + ST_A, v);
+        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
         LP_TC_ROUND(if (n_dx > 0) lp_mbar_wait(dx_free, (n_dx - 1) & 1);  // D columns 32.. hold the previous tile's last d_x0
                     LP_ISSUE(ST_A, w_och, w_ocl, 2, 2, 1024, 64, 32, wi); lp_tc_commit(bar));
         lp_tmem_ld<32>(tme + ST_D + 32, v);
@@ -496,10 +510,9 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
             lp_tmem_ld<32>(tme + ST_D, v);
             lp_tmem_zero<32>(tme + ST_D);
             const float* bl = F + I::FB + 32 * l;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bl[j], 0.f);
+            lp_bias_relu<32, LP_BWD_PK_BIAS>(v, bl);
             lp_tile_row<32>(gs + W::STK, l == 0 ? W::CH_H1 : W::CH_TR, s, v);
-            lp_stage_row<32, 32>(tme + ST_A, v);
+            lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
             // l == 1: opacity | colour hidden; the product overwrites D columns 32.., where the previous slot's d_x0 may still sit
             LP_TC_HANDOFF(if (l == 1 && n_dx > 0) lp_mbar_wait(dx_free, (n_dx - 1) & 1);
                           LP_ISSUE(ST_A, l == 0 ? w_t1h : w_och, l == 0 ? w_t1l : w_ocl, 2, 0, l == 0 ? 512 : 1024, l == 0 ? 32 : 64, 32, wi);
@@ -507,35 +520,20 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
             LP_TC_WAIT();
           }
           {  // output layer (4 wide) on the CUDA cores, exact fp32; two partial sums per output shorten the FMA chains
-            float r0 = F[I::FBL + 3], r1 = 0.f;
             lp_tmem_ld<32>(tme + ST_D, v);
             lp_tmem_zero<32>(tme + ST_D);
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              v[j] = fmaxf(v[j] + F[I::FB + 64 + j], 0.f);
-              v[j + 1] = fmaxf(v[j + 1] + F[I::FB + 64 + j + 1], 0.f);
-              r0 = fmaf(v[j], F[I::FWO + j], r0);
-              r1 = fmaf(v[j + 1], F[I::FWO + j + 1], r1);
-            }
-            raw = r0 + r1;
+            lp_bias_relu<32, LP_BWD_PK_BIAS>(v, F + I::FB + 64);
+            raw = lp_head_opacity<LP_BWD_PK_HEADS>(v, F + I::FWO, F[I::FBL + 3]);
             lp_tile_row<32>(gs + W::STK, W::CH_HO, s, v);
-            float a0 = F[I::FBL], a1 = F[I::FBL + 1], a2 = F[I::FBL + 2], b0 = 0.f, b1 = 0.f, b2 = 0.f;
             lp_tmem_ld<32>(tme + ST_D + 32, v);
             lp_tmem_zero<32>(tme + ST_D + 32);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const float4 eb = ecb[k * GT];  // enc x Wc0 + b (stands in for the bias)
-              v[4 * k] = fmaxf(v[4 * k] + eb.x, 0.f); v[4 * k + 1] = fmaxf(v[4 * k + 1] + eb.y, 0.f);
-              v[4 * k + 2] = fmaxf(v[4 * k + 2] + eb.z, 0.f); v[4 * k + 3] = fmaxf(v[4 * k + 3] + eb.w, 0.f);
+              const float2 lo = lp_add2(lp_f2(v[4 * k], v[4 * k + 1]), lp_f2(eb.x, eb.y)), hi = lp_add2(lp_f2(v[4 * k + 2], v[4 * k + 3]), lp_f2(eb.z, eb.w));
+              v[4 * k] = fmaxf(lo.x, 0.f); v[4 * k + 1] = fmaxf(lo.y, 0.f); v[4 * k + 2] = fmaxf(hi.x, 0.f); v[4 * k + 3] = fmaxf(hi.y, 0.f);
             }
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float4 w0 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
-              const float4 w1 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j + 4);
-              a0 = fmaf(v[j], w0.x, a0); a1 = fmaf(v[j], w0.y, a1); a2 = fmaf(v[j], w0.z, a2);
-              b0 = fmaf(v[j + 1], w1.x, b0); b1 = fmaf(v[j + 1], w1.y, b1); b2 = fmaf(v[j + 1], w1.z, b2);
-            }
-            lg0 = a0 + b0; lg1 = a1 + b1; lg2 = a2 + b2;
+            lp_head_colour<LP_BWD_PK_HEADS>(v, F + I::FWC, F + I::FBL, lg0, lg1, lg2);
             lp_tile_row<32>(gs + W::STK, W::CH_HC, s, v);
           }
           if (probe) {  // decoder output at zero features, for the compositing of the empty steps
@@ -563,20 +561,15 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         }
         lp_tile8(gs + W::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
         // ------------------------------ backward sweep ------------------------------
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = g_raw * F[I::FWO + j];  // d_ho
+        lp_head_opacity_bwd<LP_BWD_PK_HEADS>(v, F + I::FWO, g_raw);  // d_ho
         lp_gate_row<32>(v, gs + W::STK, W::CH_HO, s);
         lp_tile_row<32>(gs + W::DY, 4, s, v);
 #if LP_BWD_XT_TF32
         lp_stage_row_tf32<32>(tme + ST_A, v);
 #else
-        lp_stage_row<32, 32>(tme + ST_A, v);        // [d_ho | d_hc]: packed hi words at columns 0..31, lo at 32..63
+        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);        // [d_ho | d_hc]: packed hi words at columns 0..31, lo at 32..63
 #endif
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {                                     // d_hc
-          const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
-          v[j] = fmaf(dl0, w.x, fmaf(dl1, w.y, dl2 * w.z));
-        }
+        lp_head_colour_bwd<LP_BWD_PK_HEADS>(v, F + I::FWC, dl0, dl1, dl2);  // d_hc
         lp_gate_row<32>(v, gs + W::STK, W::CH_HC, s);
 #pragma unroll
         for (int j = 0; j < 32; ++j) S[j] += v[j];
@@ -585,7 +578,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         lp_stage_row_tf32<32>(tme + ST_A + 32, v);
         LP_TC_ROUND(LP_ISSUE_TF32(ST_D, ST_A, w_xt, 8, 0, 2048, 32); lp_tc_commit(bar));
 #else
-        lp_stage_row<32, 32>(tme + ST_A + 16, v);
+        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A + 16, v);
         LP_TC_ROUND(LP_ISSUE(ST_A, w_xt, w_xtl, 4, 0, 1024, 32, 32, wi); lp_tc_commit(bar));
 #endif
         // d_t and d_h1: one body (gate + dW tile + hi/lo operand + next product), executed twice; the second product (d_x0,
@@ -596,7 +589,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           lp_tmem_zero<32>(tme + ST_D);
           lp_gate_row<32>(v, gs + W::STK, l == 0 ? W::CH_TR : W::CH_H1, s);
           lp_tile_row<32>(gs + W::DY, l == 0 ? 0 : 12, s, v);
-          lp_stage_row<32, 32>(tme + ST_A, v);
+          lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
           if (l == 0) {
             LP_TC_ROUND(LP_ISSUE(ST_A, w_xhh, w_xhl, 2, 0, 512, 32, 32, wi); lp_tc_commit(bar));
           } else {
@@ -642,52 +635,35 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);  // the previous dW GEMM has consumed the tiles (long done)
         lp_tmem_ld<32>(tme + ST_D, v);
         lp_tmem_zero<32>(tme + ST_D);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + j], 0.f);
+        lp_bias_relu<32, LP_BWD_PK_BIAS>(v, F + I::FB);
         lp_tile_row<32>(gs + W::STK, W::CH_H1, s, v);
-        lp_stage_row<32, 32>(tme + ST_A, v);
+        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
         LP_TC_ROUND(LP_ISSUE(ST_A, w_t1h, w_t1l, 2, 0, 512, 32, 32, wi); lp_tc_commit(bar));
         lp_tmem_ld<32>(tme + ST_D, v);
         lp_tmem_zero<32>(tme + ST_D);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + F[I::FB + 32 + j], 0.f);
+        lp_bias_relu<32, LP_BWD_PK_BIAS>(v, F + I::FB + 32);
         lp_tile_row<32>(gs + W::STK, W::CH_TR, s, v);
-        lp_stage_row<32, 32>(tme + ST_A, v);
+        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
         // opacity | colour hidden: the product overwrites D columns 32.., where the previous slot's d_x0 may still sit
         LP_TC_HANDOFF(if (n_dx > 0) lp_mbar_wait(dx_free, (n_dx - 1) & 1);
                       LP_ISSUE(ST_A, w_och, w_ocl, 2, 0, 1024, 64, 32, wi); lp_tc_commit(bar));
         LP_TC_WAIT();
         float raw, lg0, lg1, lg2;
         {  // output layer (4 wide) on the CUDA cores, exact fp32; two partial sums per output shorten the FMA chains
-          float r0 = F[I::FBL + 3], r1 = 0.f;
           lp_tmem_ld<32>(tme + ST_D, v);
           lp_tmem_zero<32>(tme + ST_D);
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            v[j] = fmaxf(v[j] + F[I::FB + 64 + j], 0.f);
-            v[j + 1] = fmaxf(v[j + 1] + F[I::FB + 64 + j + 1], 0.f);
-            r0 = fmaf(v[j], F[I::FWO + j], r0);
-            r1 = fmaf(v[j + 1], F[I::FWO + j + 1], r1);
-          }
-          raw = r0 + r1;
+          lp_bias_relu<32, LP_BWD_PK_BIAS>(v, F + I::FB + 64);
+          raw = lp_head_opacity<LP_BWD_PK_HEADS>(v, F + I::FWO, F[I::FBL + 3]);
           lp_tile_row<32>(gs + W::STK, W::CH_HO, s, v);
-          float a0 = F[I::FBL], a1 = F[I::FBL + 1], a2 = F[I::FBL + 2], b0 = 0.f, b1 = 0.f, b2 = 0.f;
           lp_tmem_ld<32>(tme + ST_D + 32, v);
           lp_tmem_zero<32>(tme + ST_D + 32);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float4 eb = ecb[k * GT];  // enc x Wc0 + b (stands in for the bias)
-            v[4 * k] = fmaxf(v[4 * k] + eb.x, 0.f); v[4 * k + 1] = fmaxf(v[4 * k + 1] + eb.y, 0.f);
-            v[4 * k + 2] = fmaxf(v[4 * k + 2] + eb.z, 0.f); v[4 * k + 3] = fmaxf(v[4 * k + 3] + eb.w, 0.f);
+            const float2 lo = lp_add2(lp_f2(v[4 * k], v[4 * k + 1]), lp_f2(eb.x, eb.y)), hi = lp_add2(lp_f2(v[4 * k + 2], v[4 * k + 3]), lp_f2(eb.z, eb.w));
+            v[4 * k] = fmaxf(lo.x, 0.f); v[4 * k + 1] = fmaxf(lo.y, 0.f); v[4 * k + 2] = fmaxf(hi.x, 0.f); v[4 * k + 3] = fmaxf(hi.y, 0.f);
           }
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float4 w0 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
-            const float4 w1 = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j + 4);
-            a0 = fmaf(v[j], w0.x, a0); a1 = fmaf(v[j], w0.y, a1); a2 = fmaf(v[j], w0.z, a2);
-            b0 = fmaf(v[j + 1], w1.x, b0); b1 = fmaf(v[j + 1], w1.y, b1); b2 = fmaf(v[j + 1], w1.z, b2);
-          }
-          lg0 = a0 + b0; lg1 = a1 + b1; lg2 = a2 + b2;
+          lp_head_colour<LP_BWD_PK_HEADS>(v, F + I::FWC, F + I::FBL, lg0, lg1, lg2);
           lp_tile_row<32>(gs + W::STK, W::CH_HC, s, v);
         }
         if (probe) {  // decoder output at zero features, for the compositing of the empty steps
@@ -704,20 +680,15 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         else { g_raw = G_raw; dl0 = L0; dl1 = L1; dl2 = L2; }  // the summed gradients of the tile's empty steps
         lp_tile8(gs + W::DYL, 0, s, dl0, dl1, dl2, g_raw, 0.f, 0.f, 0.f, 0.f);
         // ------------------------------ backward sweep ------------------------------
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = g_raw * F[I::FWO + j];  // d_ho
+        lp_head_opacity_bwd<LP_BWD_PK_HEADS>(v, F + I::FWO, g_raw);  // d_ho
         lp_gate_row<32>(v, gs + W::STK, W::CH_HO, s);
         lp_tile_row<32>(gs + W::DY, 4, s, v);
 #if LP_BWD_XT_TF32
         lp_stage_row_tf32<32>(tme + ST_A, v);
 #else
-        lp_stage_row<32, 32>(tme + ST_A, v);        // [d_ho | d_hc]: packed hi words at columns 0..31, lo at 32..63
+        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);        // [d_ho | d_hc]: packed hi words at columns 0..31, lo at 32..63
 #endif
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {                                     // d_hc
-          const float4 w = *reinterpret_cast<const float4*>(F + I::FWC + 4 * j);
-          v[j] = fmaf(dl0, w.x, fmaf(dl1, w.y, dl2 * w.z));
-        }
+        lp_head_colour_bwd<LP_BWD_PK_HEADS>(v, F + I::FWC, dl0, dl1, dl2);  // d_hc
         lp_gate_row<32>(v, gs + W::STK, W::CH_HC, s);
 #pragma unroll
         for (int j = 0; j < 32; ++j) S[j] += v[j];
@@ -726,20 +697,20 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         lp_stage_row_tf32<32>(tme + ST_A + 32, v);
         LP_TC_ROUND(LP_ISSUE_TF32(ST_D, ST_A, w_xt, 8, 0, 2048, 32); lp_tc_commit(bar));
 #else
-        lp_stage_row<32, 32>(tme + ST_A + 16, v);
+        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A + 16, v);
         LP_TC_ROUND(LP_ISSUE(ST_A, w_xt, w_xtl, 4, 0, 1024, 32, 32, wi); lp_tc_commit(bar));
 #endif
         lp_tmem_ld<32>(tme + ST_D, v);
         lp_tmem_zero<32>(tme + ST_D);
         lp_gate_row<32>(v, gs + W::STK, W::CH_TR, s);  // d_t
         lp_tile_row<32>(gs + W::DY, 0, s, v);
-        lp_stage_row<32, 32>(tme + ST_A, v);
+        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
         LP_TC_ROUND(LP_ISSUE(ST_A, w_xhh, w_xhl, 2, 0, 512, 32, 32, wi); lp_tc_commit(bar));
         lp_tmem_ld<32>(tme + ST_D, v);
         lp_tmem_zero<32>(tme + ST_D);
         lp_gate_row<32>(v, gs + W::STK, W::CH_H1, s);  // d_h1
         lp_tile_row<32>(gs + W::DY, 12, s, v);
-        lp_stage_row<32, 32>(tme + ST_A, v);
+        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
         lp_fence_async_smem();  // this step's tile writes -> visible to the tensor core
         // last product of the slot: d_x0 (for the memory group) and the dW GEMM; nobody here waits for them
         LP_TC_HANDOFF(LP_ISSUE_D(ST_D + 32, ST_A, w_x0h, w_x0l, 2, 0, 512, C, 32, wi); lp_tc_commit(dx_full);
@@ -761,7 +732,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
 #if LP_BWD_XT_TF32
         lp_stage_row_tf32<32>(tme + ST_A + 32, S);  // K index 32..63 of the d_t weight tile = colour hidden
 #else
-        lp_stage_row<32, 32>(tme + ST_A, S);        // issued against k-steps 2, 3 of the tile (K index 32..63 = colour hidden)
+        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, S);        // issued against k-steps 2, 3 of the tile (K index 32..63 = colour hidden)
 #endif
         lp_fence_async_smem();
 #if LP_BWD_XT_TF32

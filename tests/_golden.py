@@ -112,6 +112,26 @@ def oracle_splat_case(c, dtype=torch.float64):
     return {k: v.detach() for k, v in res.items()}
 
 
+def regrid_case(c, order=(0, 1, 2), sizes=None, seed=9):
+    """Copy of a triplane renderer case with its grid LIST re-ordered (`order`) or given other plane sizes (`sizes`, fresh
+    random features): the kernels' triplane fast path must not depend on the order, and must step aside for planes that
+    do not belong to one volume."""
+    c = dict(c)
+    old = [[int(v) for v in q] for q in c["grid_sizes"]]
+    C = old[0][4]
+    if sizes is not None:
+        g = torch.Generator().manual_seed(seed)
+        new = [list(q) for q in sizes]
+        c["grid"] = torch.randn(sum(q[0] * q[1] * q[2] * q[3] for q in new), C, generator=g)
+    else:
+        rows = [q[0] * q[1] * q[2] * q[3] for q in old]
+        parts = list(torch.split(c["grid"], rows, 0))
+        new = [old[i] for i in order]
+        c["grid"] = torch.cat([parts[i] for i in order], 0)
+    c["grid_sizes"] = np.array(new)
+    return c
+
+
 def plain_splat_case(n=70, channels=32, **kw):
     """A plain (no MLP) splatter case: `synthetic_splat_case` without its MLP entries."""
     c = synthetic_splat_case(n=n, c_in=channels, c_out=channels, **kw)

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from _golden import (case_names, coherent_case, load_case, synthetic_case, oracle_render_case, oracle_splat_case, rel_err,
-                     plain_splat_case, renderer_cfg, splat_cfg)
+                     plain_splat_case, regrid_case, renderer_cfg, splat_cfg)
 from _lowlevel import render_case, splat_case
 
 pytestmark = pytest.mark.gpu
@@ -346,3 +346,21 @@ def test_gpu_plain_splatter_shared_march(lib, channels, samples, triplane, mask)
     for k, v in got.items():
         assert torch.isfinite(v).all(), k
         assert rel_err(v, want[k]) < 2e-4, (k, rel_err(v, want[k]))
+
+
+@pytest.mark.parametrize("variant", ["order_yz_xy_xz", "order_xz_yz_xy", "sizes_not_one_volume"])
+def test_gpu_triplane_fast_path_order_and_fallback(lib, variant):
+    """The triplane fast path (LpGridSet::tri) for plane lists in any order, and the generic path for three planes whose
+    axis sizes do not agree."""
+    c = synthetic_case(n=128, C=16, hidden=32, layers=(2, 2, 2), color_grid=False, plane=7, samples=9, samples_inf=2, pixel=0.05)
+    if variant == "order_yz_xy_xz":
+        c = regrid_case(c, order=(2, 0, 1))
+    elif variant == "order_xz_yz_xy":
+        c = regrid_case(c, order=(1, 2, 0))
+    else:
+        c = regrid_case(c, sizes=[[2, 1, 7, 8, 16], [2, 5, 1, 9, 16], [2, 6, 7, 1, 16]])
+    want = oracle_render_case(c)
+    got = render_case(lib, c, "cuda")
+    for k, v in got.items():
+        tol = 6e-3 if k == "g_mlp" else (1e-3 if k.startswith("g_") else 2e-4)
+        assert rel_err(v, want[k]) < tol, (variant, k, rel_err(v, want[k]))
