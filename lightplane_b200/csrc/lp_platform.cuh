@@ -82,6 +82,27 @@ LP_DEVICE unsigned lp_pack_bf16x2(float lo, float hi) {  // lo -> bits 0..15, hi
 #endif
 }
 
+// ReLU fused into the conversion / into a packed pair: max(x, 0) rounded to bf16; max(bf16 pair, 0)
+LP_DEVICE unsigned lp_pack_bf16x2_relu(float lo, float hi) {
+#if defined(LP_HOSTSIM)
+  return lp_pack_bf16x2(lo > 0.f ? lo : 0.f, hi > 0.f ? hi : 0.f);
+#else
+  unsigned r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+#endif
+}
+LP_DEVICE unsigned lp_relu_bf16x2(unsigned v) {
+#if defined(LP_HOSTSIM)
+  auto h = [](unsigned x) -> unsigned { return ((x & 0x8000u) || (x & 0x7fffu) > 0x7f80u) ? 0u : x; };  // negative or NaN -> +0
+  return h(v & 0xffffu) | (h(v >> 16) << 16);
+#else
+  unsigned r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
+  return r;
+#endif
+}
+
 // fp32 -> tf32 (10-bit mantissa) with round-to-nearest, as a 32-bit pattern; the tensor core ignores the low 13 bits
 // of a kind::tf32 operand, so feeding raw fp32 would truncate (a systematic bias of -2^-12 per factor)
 LP_DEVICE unsigned lp_tf32_rna(float x) {

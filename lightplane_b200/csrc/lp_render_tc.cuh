@@ -370,6 +370,46 @@ LP_DEVICE void lp_stage_row(unsigned taddr_a, const float (&x)[N]) {
   lp_tmem_st<N / 2>(taddr_a + LO, lo);
 }
 
+// The same with the layer's ReLU folded in (x = pre-activation): hi = max(trunc(x), 0) on the packed pair; the residual
+// x - trunc(x) has the sign of x, so the ReLU of the low part's conversion zeroes it exactly when x <= 0.  Bit-identical to
+// splitting max(x, 0), two instructions per pair cheaper.
+template <bool PK = true>
+LP_DEVICE void lp_split2_relu(float x0, float x1, unsigned& hi, unsigned& lo) {
+  hi = lp_relu_bf16x2(__byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632));
+  const float t0 = __uint_as_float(__float_as_uint(x0) & 0xffff0000u), t1 = __uint_as_float(__float_as_uint(x1) & 0xffff0000u);
+  if constexpr (PK) {
+    const float2 r = lp_sub2(lp_f2(x0, x1), lp_f2(t0, t1));
+    lo = lp_pack_bf16x2_relu(r.x, r.y);
+  } else {
+    lo = lp_pack_bf16x2_relu(x0 - t0, x1 - t1);
+  }
+}
+template <int N, int LO = 16, bool PK = true>
+LP_DEVICE void lp_stage_row_relu(unsigned taddr_a, const float (&x)[N]) {
+  unsigned hi[N / 2], lo[N / 2];
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) lp_split2_relu<PK>(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+  lp_tmem_st<N / 2>(taddr_a, hi);
+  lp_tmem_st<N / 2>(taddr_a + LO, lo);
+}
+// v[j] += bias[j] (the ReLU follows in lp_stage_row_relu / lp_tile_row_relu)
+template <int N, bool PK = true>
+LP_DEVICE void lp_bias_add(float (&v)[N], const float* bias) {
+#ifdef LP_ABL_NO_BIAS  // timing experiment only (wrong results): what preloading the bias into the accumulator could save
+  return;
+#endif
+#pragma unroll
+  for (int k = 0; k < N / 4; ++k) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * k);
+    if constexpr (PK) {
+      const float2 lo = lp_add2(lp_f2(v[4 * k], v[4 * k + 1]), lp_f2(b.x, b.y)), hi = lp_add2(lp_f2(v[4 * k + 2], v[4 * k + 3]), lp_f2(b.z, b.w));
+      v[4 * k] = lo.x; v[4 * k + 1] = lo.y; v[4 * k + 2] = hi.x; v[4 * k + 3] = hi.y;
+    } else {
+      v[4 * k] += b.x; v[4 * k + 1] += b.y; v[4 * k + 2] += b.z; v[4 * k + 3] += b.w;
+    }
+  }
+}
+
 // ---- decoder epilogue arithmetic on packed fp32 pairs (same roundings as the scalar forms; lp_platform.cuh) ----
 // v[j] = max(v[j] + bias[j], 0) for a row of N accumulator values (bias in shared memory, 16-byte aligned)
 template <int N, bool PK = true>
@@ -531,7 +571,14 @@ LP_DEVICE bool lp_gather_regs(const LpGridSet& G, int b, float x, float y, float
         }
       }
     }
-  } else
+    const float2 ob = lp_f2(oob, oob);
+#pragma unroll
+    for (int c = 0; c < CW; c += 2) {
+      const float2 t = lp_mul2(lp_f2(acc[c], acc[c + 1]), ob);
+      acc[c] = t.x; acc[c + 1] = t.y;
+    }
+    return hit && oob != 0.f;
+  }
   for (int gi = 0; gi < G.n; ++gi) {
     int off[8];
     float w[8];
@@ -668,8 +715,8 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
       lp_tc_fence_after();
       lp_tmem_ld32u(tme + TC_D, v);
       lp_tmem_zero<32>(tme + TC_D);
-      lp_bias_relu<32>(v, F + I::FB);
-      lp_stage_row<32>(tme + TC_A, v);
+      lp_bias_add<32>(v, F + I::FB);
+      lp_stage_row_relu<32>(tme + TC_A, v);
       // ---- trunk layer 1 ----
       lp_tmem_wait_st();
       lp_tc_fence_before();
@@ -683,8 +730,8 @@ __global__ void __launch_bounds__(LP_TC_FWD_GROUPS * 128, 1) lp_render_fwd_tc_ke
       lp_tc_fence_after();
       lp_tmem_ld32u(tme + TC_D, v);
       lp_tmem_zero<32>(tme + TC_D);
-      lp_bias_relu<32>(v, F + I::FB + 32);
-      lp_stage_row<32>(tme + TC_A, v);
+      lp_bias_add<32>(v, F + I::FB + 32);
+      lp_stage_row_relu<32>(tme + TC_A, v);
       // ---- opacity + colour hidden layers: trunk (K = 32) x [64 outputs]; the encoding's share comes from `ecb` ----
       lp_tmem_wait_st();
       lp_tc_fence_before();
@@ -805,6 +852,18 @@ LP_DEVICE void lp_tile_row(unsigned char* tile, int chunk0, int s, const float (
 #pragma unroll
   for (int c = 0; c < N / 8; ++c)
     lp_tile8(tile, chunk0 + c, s, x[8 * c], x[8 * c + 1], x[8 * c + 2], x[8 * c + 3], x[8 * c + 4], x[8 * c + 5], x[8 * c + 6], x[8 * c + 7]);
+}
+// the same with max(x, 0) folded into the conversion
+template <int N>
+LP_DEVICE void lp_tile_row_relu(unsigned char* tile, int chunk0, int s, const float (&x)[N]) {
+#ifdef LP_ABL_NO_TILES
+  return;
+#endif
+#pragma unroll
+  for (int c = 0; c < N / 8; ++c)
+    *reinterpret_cast<uint4*>(tile + (chunk0 + c) * 2048 + (s >> 3) * 128 + (s & 7) * 16) =
+        make_uint4(lp_pack_bf16x2_relu(x[8 * c], x[8 * c + 1]), lp_pack_bf16x2_relu(x[8 * c + 2], x[8 * c + 3]),
+                   lp_pack_bf16x2_relu(x[8 * c + 4], x[8 * c + 5]), lp_pack_bf16x2_relu(x[8 * c + 6], x[8 * c + 7]));
 }
 template <int N>
 LP_DEVICE unsigned lp_mask_pos(const float (&x)[N]) {

@@ -510,9 +510,9 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
             lp_tmem_ld<32>(tme + ST_D, v);
             lp_tmem_zero<32>(tme + ST_D);
             const float* bl = F + I::FB + 32 * l;
-            lp_bias_relu<32, LP_BWD_PK_BIAS>(v, bl);
-            lp_tile_row<32>(gs + W::STK, l == 0 ? W::CH_H1 : W::CH_TR, s, v);
-            lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
+            lp_bias_add<32, LP_BWD_PK_BIAS>(v, bl);  // the ReLU rides on the two conversions below
+            lp_tile_row_relu<32>(gs + W::STK, l == 0 ? W::CH_H1 : W::CH_TR, s, v);
+            lp_stage_row_relu<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
             // l == 1: opacity | colour hidden; the product overwrites D columns 32.., where the previous slot's d_x0 may still sit
             LP_TC_HANDOFF(if (l == 1 && n_dx > 0) lp_mbar_wait(dx_free, (n_dx - 1) & 1);
                           LP_ISSUE(ST_A, l == 0 ? w_t1h : w_och, l == 0 ? w_t1l : w_ocl, 2, 0, l == 0 ? 512 : 1024, l == 0 ? 32 : 64, 32, wi);
@@ -572,7 +572,10 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         lp_head_colour_bwd<LP_BWD_PK_HEADS>(v, F + I::FWC, dl0, dl1, dl2);  // d_hc
         lp_gate_row<32>(v, gs + W::STK, W::CH_HC, s);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) S[j] += v[j];
+        for (int j = 0; j < 32; j += 2) {
+          const float2 t = lp_add2(lp_f2(S[j], S[j + 1]), lp_f2(v[j], v[j + 1]));
+          S[j] = t.x; S[j + 1] = t.y;
+        }
         lp_tile_row<32>(gs + W::DY, 8, s, v);
 #if LP_BWD_XT_TF32
         lp_stage_row_tf32<32>(tme + ST_A + 32, v);
@@ -635,15 +638,15 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         if (n_dw > 0) lp_mbar_wait(bar_dw, (n_dw - 1) & 1);  // the previous dW GEMM has consumed the tiles (long done)
         lp_tmem_ld<32>(tme + ST_D, v);
         lp_tmem_zero<32>(tme + ST_D);
-        lp_bias_relu<32, LP_BWD_PK_BIAS>(v, F + I::FB);
-        lp_tile_row<32>(gs + W::STK, W::CH_H1, s, v);
-        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
+        lp_bias_add<32, LP_BWD_PK_BIAS>(v, F + I::FB);
+        lp_tile_row_relu<32>(gs + W::STK, W::CH_H1, s, v);
+        lp_stage_row_relu<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
         LP_TC_ROUND(LP_ISSUE(ST_A, w_t1h, w_t1l, 2, 0, 512, 32, 32, wi); lp_tc_commit(bar));
         lp_tmem_ld<32>(tme + ST_D, v);
         lp_tmem_zero<32>(tme + ST_D);
-        lp_bias_relu<32, LP_BWD_PK_BIAS>(v, F + I::FB + 32);
-        lp_tile_row<32>(gs + W::STK, W::CH_TR, s, v);
-        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
+        lp_bias_add<32, LP_BWD_PK_BIAS>(v, F + I::FB + 32);
+        lp_tile_row_relu<32>(gs + W::STK, W::CH_TR, s, v);
+        lp_stage_row_relu<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
         // opacity | colour hidden: the product overwrites D columns 32.., where the previous slot's d_x0 may still sit
         LP_TC_HANDOFF(if (n_dx > 0) lp_mbar_wait(dx_free, (n_dx - 1) & 1);
                       LP_ISSUE(ST_A, w_och, w_ocl, 2, 0, 1024, 64, 32, wi); lp_tc_commit(bar));
@@ -691,7 +694,10 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         lp_head_colour_bwd<LP_BWD_PK_HEADS>(v, F + I::FWC, dl0, dl1, dl2);  // d_hc
         lp_gate_row<32>(v, gs + W::STK, W::CH_HC, s);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) S[j] += v[j];
+        for (int j = 0; j < 32; j += 2) {
+          const float2 t = lp_add2(lp_f2(S[j], S[j + 1]), lp_f2(v[j], v[j + 1]));
+          S[j] = t.x; S[j + 1] = t.y;
+        }
         lp_tile_row<32>(gs + W::DY, 8, s, v);
 #if LP_BWD_XT_TF32
         lp_stage_row_tf32<32>(tme + ST_A + 32, v);
