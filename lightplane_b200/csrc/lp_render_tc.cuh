@@ -853,6 +853,26 @@ LP_DEVICE void lp_tile_row(unsigned char* tile, int chunk0, int s, const float (
   for (int c = 0; c < N / 8; ++c)
     lp_tile8(tile, chunk0 + c, s, x[8 * c], x[8 * c + 1], x[8 * c + 2], x[8 * c + 3], x[8 * c + 4], x[8 * c + 5], x[8 * c + 6], x[8 * c + 7]);
 }
+// A row that goes BOTH into a dW tile (bf16, round-to-nearest) and into the A operand (hi + lo): the tile's conversion
+// is the operand's hi part (round-to-nearest instead of the truncation of lp_split2: the residual is then at most half a
+// bf16 ulp), so a pair costs one conversion less than lp_tile_row + lp_stage_row.
+template <int N, int LO = 16>
+LP_DEVICE void lp_tile_stage_row(unsigned char* tile, int chunk0, int s, unsigned taddr_a, const float (&x)[N]) {
+  unsigned hi[N / 2], lo[N / 2];
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) {
+    hi[j] = lp_pack_bf16x2(x[2 * j], x[2 * j + 1]);
+    const float2 r = lp_sub2(lp_f2(x[2 * j], x[2 * j + 1]), lp_f2(__uint_as_float(hi[j] << 16), __uint_as_float(hi[j] & 0xffff0000u)));
+    lo[j] = lp_pack_bf16x2(r.x, r.y);
+  }
+#ifndef LP_ABL_NO_TILES
+#pragma unroll
+  for (int c = 0; c < N / 8; ++c)
+    *reinterpret_cast<uint4*>(tile + (chunk0 + c) * 2048 + (s >> 3) * 128 + (s & 7) * 16) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+#endif
+  lp_tmem_st<N / 2>(taddr_a, hi);
+  lp_tmem_st<N / 2>(taddr_a + LO, lo);
+}
 // the same with max(x, 0) folded into the conversion
 template <int N>
 LP_DEVICE void lp_tile_row_relu(unsigned char* tile, int chunk0, int s, const float (&x)[N]) {

@@ -563,11 +563,11 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         // ------------------------------ backward sweep ------------------------------
         lp_head_opacity_bwd<LP_BWD_PK_HEADS>(v, F + I::FWO, g_raw);  // d_ho
         lp_gate_row<32>(v, gs + W::STK, W::CH_HO, s);
-        lp_tile_row<32>(gs + W::DY, 4, s, v);
 #if LP_BWD_XT_TF32
+        lp_tile_row<32>(gs + W::DY, 4, s, v);
         lp_stage_row_tf32<32>(tme + ST_A, v);
 #else
-        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);        // [d_ho | d_hc]: packed hi words at columns 0..31, lo at 32..63
+        lp_tile_stage_row<32, 32>(gs + W::DY, 4, s, tme + ST_A, v);  // [d_ho | d_hc]: packed hi words at columns 0..31, lo at 32..63
 #endif
         lp_head_colour_bwd<LP_BWD_PK_HEADS>(v, F + I::FWC, dl0, dl1, dl2);  // d_hc
         lp_gate_row<32>(v, gs + W::STK, W::CH_HC, s);
@@ -576,12 +576,12 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           const float2 t = lp_add2(lp_f2(S[j], S[j + 1]), lp_f2(v[j], v[j + 1]));
           S[j] = t.x; S[j + 1] = t.y;
         }
-        lp_tile_row<32>(gs + W::DY, 8, s, v);
 #if LP_BWD_XT_TF32
+        lp_tile_row<32>(gs + W::DY, 8, s, v);
         lp_stage_row_tf32<32>(tme + ST_A + 32, v);
         LP_TC_ROUND(LP_ISSUE_TF32(ST_D, ST_A, w_xt, 8, 0, 2048, 32); lp_tc_commit(bar));
 #else
-        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A + 16, v);
+        lp_tile_stage_row<32, 32>(gs + W::DY, 8, s, tme + ST_A + 16, v);
         LP_TC_ROUND(LP_ISSUE(ST_A, w_xt, w_xtl, 4, 0, 1024, 32, 32, wi); lp_tc_commit(bar));
 #endif
         // d_t and d_h1: one body (gate + dW tile + hi/lo operand + next product), executed twice; the second product (d_x0,
@@ -591,8 +591,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           lp_tmem_ld<32>(tme + ST_D, v);
           lp_tmem_zero<32>(tme + ST_D);
           lp_gate_row<32>(v, gs + W::STK, l == 0 ? W::CH_TR : W::CH_H1, s);
-          lp_tile_row<32>(gs + W::DY, l == 0 ? 0 : 12, s, v);
-          lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
+          lp_tile_stage_row<32, 32>(gs + W::DY, l == 0 ? 0 : 12, s, tme + ST_A, v);
           if (l == 0) {
             LP_TC_ROUND(LP_ISSUE(ST_A, w_xhh, w_xhl, 2, 0, 512, 32, 32, wi); lp_tc_commit(bar));
           } else {
@@ -685,11 +684,11 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
         // ------------------------------ backward sweep ------------------------------
         lp_head_opacity_bwd<LP_BWD_PK_HEADS>(v, F + I::FWO, g_raw);  // d_ho
         lp_gate_row<32>(v, gs + W::STK, W::CH_HO, s);
-        lp_tile_row<32>(gs + W::DY, 4, s, v);
 #if LP_BWD_XT_TF32
+        lp_tile_row<32>(gs + W::DY, 4, s, v);
         lp_stage_row_tf32<32>(tme + ST_A, v);
 #else
-        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);        // [d_ho | d_hc]: packed hi words at columns 0..31, lo at 32..63
+        lp_tile_stage_row<32, 32>(gs + W::DY, 4, s, tme + ST_A, v);  // [d_ho | d_hc]: packed hi words at columns 0..31, lo at 32..63
 #endif
         lp_head_colour_bwd<LP_BWD_PK_HEADS>(v, F + I::FWC, dl0, dl1, dl2);  // d_hc
         lp_gate_row<32>(v, gs + W::STK, W::CH_HC, s);
@@ -698,25 +697,23 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
           const float2 t = lp_add2(lp_f2(S[j], S[j + 1]), lp_f2(v[j], v[j + 1]));
           S[j] = t.x; S[j + 1] = t.y;
         }
-        lp_tile_row<32>(gs + W::DY, 8, s, v);
 #if LP_BWD_XT_TF32
+        lp_tile_row<32>(gs + W::DY, 8, s, v);
         lp_stage_row_tf32<32>(tme + ST_A + 32, v);
         LP_TC_ROUND(LP_ISSUE_TF32(ST_D, ST_A, w_xt, 8, 0, 2048, 32); lp_tc_commit(bar));
 #else
-        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A + 16, v);
+        lp_tile_stage_row<32, 32>(gs + W::DY, 8, s, tme + ST_A + 16, v);
         LP_TC_ROUND(LP_ISSUE(ST_A, w_xt, w_xtl, 4, 0, 1024, 32, 32, wi); lp_tc_commit(bar));
 #endif
         lp_tmem_ld<32>(tme + ST_D, v);
         lp_tmem_zero<32>(tme + ST_D);
         lp_gate_row<32>(v, gs + W::STK, W::CH_TR, s);  // d_t
-        lp_tile_row<32>(gs + W::DY, 0, s, v);
-        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
+        lp_tile_stage_row<32, 32>(gs + W::DY, 0, s, tme + ST_A, v);
         LP_TC_ROUND(LP_ISSUE(ST_A, w_xhh, w_xhl, 2, 0, 512, 32, 32, wi); lp_tc_commit(bar));
         lp_tmem_ld<32>(tme + ST_D, v);
         lp_tmem_zero<32>(tme + ST_D);
         lp_gate_row<32>(v, gs + W::STK, W::CH_H1, s);  // d_h1
-        lp_tile_row<32>(gs + W::DY, 12, s, v);
-        lp_stage_row<32, 32, LP_BWD_PK_SPLIT>(tme + ST_A, v);
+        lp_tile_stage_row<32, 32>(gs + W::DY, 12, s, tme + ST_A, v);
         lp_fence_async_smem();  // this step's tile writes -> visible to the tensor core
         // last product of the slot: d_x0 (for the memory group) and the dW GEMM; nobody here waits for them
         LP_TC_HANDOFF(LP_ISSUE_D(ST_D + 32, ST_A, w_x0h, w_x0l, 2, 0, 512, C, 32, wi); lp_tc_commit(dx_full);
