@@ -23,7 +23,8 @@
 #include "lp_render_generic.cuh"
 
 #ifndef LP_TC_FWD_GROUPS
-#define LP_TC_FWD_GROUPS 4  // groups of 128 threads per CTA in the forward kernel (TMEM: 128 columns each)
+#define LP_TC_FWD_GROUPS 5  // groups of 128 threads per CTA in the forward kernel (TMEM: 96 columns each = 480 of 512; 96 registers
+                            // per thread.  4 groups at 128 registers: 10.2 ms, 5 groups: 9.4 ms once the instruction count had come down)
 #endif
 #ifndef LP_TC_EMPTY_FOLD
 #define LP_TC_EMPTY_FOLD 1  // reuse the decoder's zero-feature output at steps where a whole group is in empty space
