@@ -12,9 +12,11 @@
 // (tools/tc_test3.cu).  The accumulator comes back with tcgen05.ld as one 32-wide row per thread, so
 // bias, ReLU, the next split and finally the 4-wide output layer and the compositing are plain
 // per-thread code: no fragment layouts, no shuffles, no shared-memory transposes.  The colour branch's
-// "trunk + ray encoding" input is fed as a K = 64 product [trunk | encoding] x [Wc0; Wc0], with the
-// encoding staged in tensor memory once per ray; opacity and colour hidden layers share one N = 64 MMA.
+// "trunk + ray encoding" input: the encoding's share enc x Wc0 + b is a per-ray constant, one product per ray tile,
+// kept in shared memory and added where the bias would be; opacity and colour hidden layers share one N = 64 MMA.
 // Several groups per CTA keep the tensor pipe and the issue slots busy while a group waits for its MMA.
+// The epilogue arithmetic is written for issue slots: elect.sync issuers with warp-uniform operands,
+// packed fp32 pairs, ReLU folded into the bf16 conversions, a triplane gather that shares the axes between planes.
 //
 // Reference semantics: lightplane/triton_src/templates/renderer_fw.py:85-375 (forward) with the MLP
 // of triton_src/shared/fwbw_util.py:26-150; see DESIGN.md section 4.
