@@ -181,7 +181,8 @@ LP_DEVICE void lp_ws_issue_encw_part(unsigned tmem, unsigned char* gs, int wi) {
 #endif
 // Register split between the roles (setmaxnreg; the two values add up to 256 = 64 K registers / 256 threads per role).
 // C = 16: 168 / 88 (splits down to 152 / 104 measure the same); C = 32: the memory threads hold two 32-float rows and spill at
-// 88 registers -- 128 / 128 (no re-allocation at all) makes the cfg5 backward 140.0 -> 118.4 ms (152/104: 132.4, 136/120: 120.3).
+// 88 registers -- 128 / 128 (no re-allocation at all) makes the cfg5 backward 140.0 -> 118.4 ms (152/104: 132.4, 136/120: 120.3);
+// giving the memory threads more than the decoder threads loses again (final build: 128/128 110.8 ms, 120/136 115.2, 112/144 117.2).
 #ifndef LP_WS_REGS_MEM
 #define LP_WS_REGS_MEM(C) ((C) == 16 ? 88 : 128)
 #endif
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
     // =================================================================================================================
 #if LP_MEM_SINGLE_LOOP
     if constexpr (LP_WS_REGS_MEM(C) < 128) LP_SETMAXNREG_DEC(LP_WS_REGS_MEM(C));
+    if constexpr (LP_WS_REGS_MEM(C) > 128) LP_SETMAXNREG_INC(LP_WS_REGS_MEM(C));
     int n_slot = 0, n_dw = 0, n_dx = 0;  // slots staged; dW GEMMs the decoder group has issued; d_x0 rows consumed
     for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
       const Ray1 me = lp_load_ray1(R, lp_tile_ray(M, tile, s), G.g[0].B);
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
     }
 #else
     if constexpr (LP_WS_REGS_MEM(C) < 128) LP_SETMAXNREG_DEC(LP_WS_REGS_MEM(C));
+    if constexpr (LP_WS_REGS_MEM(C) > 128) LP_SETMAXNREG_INC(LP_WS_REGS_MEM(C));
     int n_slot = 0, n_dw = 0, n_dx = 0;  // slots staged; dW GEMMs the decoder group has issued; d_x0 rows consumed
     for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
       const Ray1 me = lp_load_ray1(R, lp_tile_ray(M, tile, s), G.g[0].B);
@@ -429,6 +432,7 @@ __global__ void __launch_bounds__(512, 1) lp_render_bwd_ws_kernel(LpRays R, LpMa
     // decoder group
     // =================================================================================================================
     if constexpr (LP_WS_REGS_MLP(C) > 128) LP_SETMAXNREG_INC(LP_WS_REGS_MLP(C));
+    if constexpr (LP_WS_REGS_MLP(C) < 128) LP_SETMAXNREG_DEC(LP_WS_REGS_MLP(C));
     // one elected lane (elect.sync) of each of the group's four warps issues its share of every product
     const int wi = wig;
     const float* F = reinterpret_cast<const float*>(sm + I::F32);
